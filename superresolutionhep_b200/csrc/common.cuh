@@ -1,0 +1,51 @@
+// Shared device helpers and parameter structs for the srhep sm_100a kernels.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace srhep {
+
+constexpr float kLnEps = 1e-5f;      // nn.LayerNorm default eps (models/dense.py:62)
+constexpr float kLeaky = 0.01f;      // nn.LeakyReLU default slope
+
+__device__ __forceinline__ float leaky_relu(float x) { return x > 0.f ? x : kLeaky * x; }
+__device__ __forceinline__ float silu(float x) { return x / (1.f + expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// One ODE stage = one network evaluation followed by `out = base + coef * v`.
+// Lives in device memory so that a captured CUDA graph of one evaluation can be replayed
+// for every stage: kernels read sp[*stage_idx].
+struct StageParams {
+    float        t;       // time of this evaluation (all events of a sampling pass share it)
+    float        coef;    // dt (euler / 2nd midpoint stage) or dt/2 (1st midpoint stage)
+    const float* x_in;    // network input state (packed rows of this pass)
+    const float* base;    // y0 of the update (may be null when out is null)
+    float*       out;     // base + coef*v (may be null)
+    float*       vout;    // raw velocity (may be null)
+};
+
+// Epilogue description shared by the fp32 and the bf16 GEMM kernels:
+//   val = act(acc + bias[n] + row_bias[event(row)][n])
+//   C   = resid ? resid[row][n] + gate[event(row)][n] * val : val
+struct GemmEpilogue {
+    const float* bias        = nullptr;
+    const float* row_bias    = nullptr;  int ld_row_bias = 0;
+    const int*   row_event   = nullptr;  // null: event(row) = row
+    int          act         = 0;        // 0 none, 1 LeakyReLU(0.01)
+    const float* gate        = nullptr;  int ld_gate = 0;
+    const float* resid       = nullptr;  int ld_resid = 0;
+};
+
+}  // namespace srhep

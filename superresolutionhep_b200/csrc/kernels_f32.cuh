@@ -1,0 +1,720 @@
+// fp32 CUDA-core kernels: per-event preparation, cell embedding, context, LayerNorm +
+// adaLN modulation, generic GEMM with fused epilogue, varlen attention, velocity head and
+// the fused ODE update.  In SRHEP_PREC_FP32 ('highest') mode these are the whole path; in
+// SRHEP_PREC_BF16 mode the dense contractions move to the tcgen05 kernels and these keep the
+// LayerNorm / embedding / head / update work (all fp32 statistics).
+//
+// Every kernel works on PACKED rows (real cells only); events are addressed through
+// cu_seqlens-derived maps, never through padding masks (SURVEY §7 "skip instead of mask").
+#pragma once
+#include "common.cuh"
+
+namespace srhep {
+
+constexpr int kMaxHid  = 64;    // hidden width of the four embedding nets (register tile)
+constexpr int kChunk   = 32;    // cells per embedding CTA
+constexpr int kMaxTemb = 128;
+constexpr int kMaxFreq = 512;
+
+// One Dense(d + t_emb -> hid -> out), LayerNorm (no affine) in front of the first Linear
+// (models/dense.py:49-78 with the embed configs of configs/*/model_and_var.yml:20-68).
+struct EmbedNetDev {
+    const float* w1;   // [hid, d + t_emb]
+    const float* b1;   // [hid]
+    const float* r1;   // [hid]  sum_k w1[j, d + k]  (precomputed on the host)
+    const float* w2;   // [out, hid]
+    const float* b2;   // [out]
+    int d, hid, out;
+};
+
+__device__ __forceinline__ void store_out(float* p, float v) { *p = v; }
+__device__ __forceinline__ void store_out(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// out_s[j] = act(sum_k W[j, k] * in_s[k] + bias[j]);  one warp per output row.
+// act: 0 none, 1 LeakyReLU, 2 SiLU.  Caller syncs before and after.
+__device__ __forceinline__ void block_matvec(const float* __restrict__ W, int ldw, const float* in_s, int K,
+                                             float* out_s, int N, const float* __restrict__ bias, int act) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int j = warp; j < N; j += nw) {
+        float acc = 0.f;
+        for (int k = lane; k < K; k += 32) acc = fmaf(__ldg(W + (size_t)j * ldw + k), in_s[k], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            if (bias) acc += __ldg(bias + j);
+            out_s[j] = act == 1 ? leaky_relu(acc) : (act == 2 ? silu(acc) : acc);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// 1. per-event preparation: timestep embedding (models/utils.py:128-166), the context
+//    part of the first Linear of each embedding net, and the full layer-embedding net
+//    for the three possible layer ids (models/flow_model.py:192-193).
+// ------------------------------------------------------------------------------------
+struct EventPrepParams {
+    const float* freqs; int half;
+    const float* wt0; const float* bt0;
+    const float* wt2; const float* bt2;
+    int t_emb;
+    EmbedNetDev etaphi, layer, proxy, noisy;
+    const float* layer_table; int layer_emb_dim;
+    float* temb;        // [B, t_emb]
+    float* ev_a;        // [B, 3, kMaxHid]   etaphi / proxy / noisy
+    float* ev_stats;    // [B, 2]            mean(temb), sum (temb - mean)^2
+    float* layer_out;   // [B, 3, layer.out]
+    const float* t_event;
+    const StageParams* sp; const int* stage_idx;
+    int e0;
+};
+
+__global__ void __launch_bounds__(128) event_prep_kernel(EventPrepParams p) {
+    __shared__ float s_sin[kMaxFreq];
+    __shared__ float s_h[kMaxTemb];
+    __shared__ float s_temb[kMaxTemb];
+    __shared__ float s_a[kMaxHid];
+    __shared__ float s_hid[kMaxHid];
+    __shared__ float s_stat[2];
+    const int tid = threadIdx.x;
+    const int e = p.e0 + blockIdx.x;
+    const float t = p.t_event ? p.t_event[e] : p.sp[*p.stage_idx].t;
+
+    for (int i = tid; i < p.half; i += blockDim.x) {
+        const float a = t * __ldg(p.freqs + i);
+        s_sin[i] = cosf(a);
+        s_sin[p.half + i] = sinf(a);
+    }
+    __syncthreads();
+    block_matvec(p.wt0, 2 * p.half, s_sin, 2 * p.half, s_h, p.t_emb, p.bt0, 2);
+    __syncthreads();
+    block_matvec(p.wt2, p.t_emb, s_h, p.t_emb, s_temb, p.t_emb, p.bt2, 0);
+    __syncthreads();
+    if (tid < 32) {
+        float s = 0.f;
+        for (int k = tid; k < p.t_emb; k += 32) s += s_temb[k];
+        s = warp_sum(s);
+        const float mt = s / (float)p.t_emb;
+        float q = 0.f;
+        for (int k = tid; k < p.t_emb; k += 32) { const float d = s_temb[k] - mt; q = fmaf(d, d, q); }
+        q = warp_sum(q);
+        if (tid == 0) {
+            s_stat[0] = mt; s_stat[1] = q;
+            p.ev_stats[2 * (size_t)e] = mt; p.ev_stats[2 * (size_t)e + 1] = q;
+        }
+    }
+    for (int k = tid; k < p.t_emb; k += blockDim.x) p.temb[(size_t)e * p.t_emb + k] = s_temb[k];
+    __syncthreads();
+
+    const EmbedNetDev* nets[3] = {&p.etaphi, &p.proxy, &p.noisy};
+#pragma unroll
+    for (int n = 0; n < 3; ++n) {
+        const EmbedNetDev& net = *nets[n];
+        block_matvec(net.w1 + net.d, net.d + p.t_emb, s_temb, p.t_emb, s_a, net.hid, nullptr, 0);
+        __syncthreads();
+        for (int j = tid; j < net.hid; j += blockDim.x) p.ev_a[((size_t)e * 3 + n) * kMaxHid + j] = s_a[j];
+        __syncthreads();
+    }
+
+    // layer-embedding net, evaluated for layer ids 0, 1, 2
+    const EmbedNetDev& L = p.layer;
+    block_matvec(L.w1 + L.d, L.d + p.t_emb, s_temb, p.t_emb, s_a, L.hid, nullptr, 0);
+    __syncthreads();
+    const float mt = s_stat[0], vt = s_stat[1];
+    const float nfeat = (float)(L.d + p.t_emb);
+    for (int l = 0; l < 3; ++l) {
+        const float* x = p.layer_table + l * p.layer_emb_dim;
+        float sx = 0.f;
+        for (int i = 0; i < L.d; ++i) sx += __ldg(x + i);
+        const float mu = (sx + (float)p.t_emb * mt) / nfeat;
+        float q = vt + (float)p.t_emb * (mt - mu) * (mt - mu);
+        for (int i = 0; i < L.d; ++i) { const float d = __ldg(x + i) - mu; q = fmaf(d, d, q); }
+        const float rstd = 1.0f / sqrtf(q / nfeat + kLnEps);
+        for (int j = tid; j < L.hid; j += blockDim.x) {
+            float acc = s_a[j] - mu * __ldg(L.r1 + j);
+            for (int i = 0; i < L.d; ++i) acc = fmaf(__ldg(L.w1 + (size_t)j * (L.d + p.t_emb) + i), __ldg(x + i) - mu, acc);
+            s_hid[j] = leaky_relu(fmaf(rstd, acc, __ldg(L.b1 + j)));
+        }
+        __syncthreads();
+        block_matvec(L.w2, L.hid, s_hid, L.hid, s_h, L.out, L.b2, 1);
+        __syncthreads();
+        for (int o = tid; o < L.out; o += blockDim.x) p.layer_out[((size_t)e * 3 + l) * L.out + o] = s_h[o];
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// 2. per-cell embedding: etaphi / proxy / noisy Dense nets + layer gather + raw e_proxy
+//    -> tok_feat[row] = [cond_feat (cond) | noisy_emb (noisy_out)]
+//    (models/flow_model.py:192-215) and per-chunk column sums for the masked mean (:210).
+//    LayerNorm over cat[x_cell, time_emb] is evaluated from the per-event statistics of
+//    time_emb, and Linear(cat[..]) splits into a per-cell part and the per-event ev_a.
+// ------------------------------------------------------------------------------------
+struct EmbedTokParams {
+    EmbedNetDev etaphi, proxy, noisy;
+    int layer_out_dim, t_emb, cond, ncol;
+    const float *eta, *cosphi, *sinphi, *e_proxy; const int* layer;
+    const float* x_in_fixed;
+    const StageParams* sp; const int* stage_idx;
+    const float* ev_a; const float* ev_stats; const float* layer_out;
+    const int *chunk_event, *chunk_row, *chunk_len;
+    float* tok_feat; int ld;
+    float* partial;
+};
+
+__global__ void __launch_bounds__(192) embed_tokens_kernel(EmbedTokParams p) {
+    __shared__ float s_x[kChunk][5];                 // eta, cosphi, sinphi, e_proxy, x_t
+    __shared__ int   s_layer[kChunk];
+    __shared__ float s_mu[kChunk][3], s_rs[kChunk][3];
+    __shared__ float s_hid[kChunk][3 * kMaxHid + 1];
+    const int tid = threadIdx.x;
+    const int c = blockIdx.x;
+    const int e = p.chunk_event[c], r0 = p.chunk_row[c], len = p.chunk_len[c];
+    const float* x_in = p.x_in_fixed ? p.x_in_fixed : p.sp[*p.stage_idx].x_in;
+
+    for (int i = tid; i < len * 6; i += blockDim.x) {
+        const int tok = i / 6, f = i % 6;
+        const size_t r = (size_t)r0 + tok;
+        if (f == 0) s_x[tok][0] = p.eta[r];
+        else if (f == 1) s_x[tok][1] = p.cosphi[r];
+        else if (f == 2) s_x[tok][2] = p.sinphi[r];
+        else if (f == 3) s_x[tok][3] = p.e_proxy[r];
+        else if (f == 4) s_x[tok][4] = x_in[r];
+        else s_layer[tok] = p.layer[r];
+    }
+    __syncthreads();
+    const float mt = p.ev_stats[2 * (size_t)e], vt = p.ev_stats[2 * (size_t)e + 1];
+    const float te = (float)p.t_emb;
+    for (int i = tid; i < len * 3; i += blockDim.x) {
+        const int tok = i / 3, n = i % 3;
+        float mu, q;
+        if (n == 0) {
+            const float a = s_x[tok][0], b = s_x[tok][1], cc = s_x[tok][2];
+            const float nf = 3.f + te;
+            mu = (a + b + cc + te * mt) / nf;
+            q = vt + te * (mt - mu) * (mt - mu) + (a - mu) * (a - mu) + (b - mu) * (b - mu) + (cc - mu) * (cc - mu);
+            q /= nf;
+        } else {
+            const float a = s_x[tok][n == 1 ? 3 : 4];
+            const float nf = 1.f + te;
+            mu = (a + te * mt) / nf;
+            q = (vt + te * (mt - mu) * (mt - mu) + (a - mu) * (a - mu)) / nf;
+        }
+        s_mu[tok][n] = mu;
+        s_rs[tok][n] = 1.0f / sqrtf(q + kLnEps);
+    }
+    __syncthreads();
+    // hidden activations of the three per-cell nets
+    for (int idx = tid; idx < 3 * kMaxHid; idx += blockDim.x) {
+        const int n = idx / kMaxHid, j = idx % kMaxHid;
+        const EmbedNetDev& net = n == 0 ? p.etaphi : (n == 1 ? p.proxy : p.noisy);
+        if (j >= net.hid) continue;
+        const float a = p.ev_a[((size_t)e * 3 + n) * kMaxHid + j];
+        const float r1 = __ldg(net.r1 + j), b1 = __ldg(net.b1 + j);
+        const float* w = net.w1 + (size_t)j * (net.d + p.t_emb);
+        const float w0 = __ldg(w), w1 = n == 0 ? __ldg(w + 1) : 0.f, w2 = n == 0 ? __ldg(w + 2) : 0.f;
+        for (int tok = 0; tok < len; ++tok) {
+            const float mu = s_mu[tok][n];
+            float acc = a - mu * r1;
+            if (n == 0) {
+                acc = fmaf(w0, s_x[tok][0] - mu, acc);
+                acc = fmaf(w1, s_x[tok][1] - mu, acc);
+                acc = fmaf(w2, s_x[tok][2] - mu, acc);
+            } else {
+                acc = fmaf(w0, s_x[tok][n == 1 ? 3 : 4] - mu, acc);
+            }
+            s_hid[tok][idx] = leaky_relu(fmaf(s_rs[tok][n], acc, b1));
+        }
+    }
+    __syncthreads();
+    // output columns: one thread per column, weights of its row in registers
+    const int col = tid;
+    if (col < p.ncol) {
+        const int eo = p.etaphi.out, lo = p.layer_out_dim, po = p.proxy.out;
+        int kind, o = 0, hoff = 0;                       // kind: 0 net, 1 layer gather, 2 raw e_proxy
+        const EmbedNetDev* net = nullptr;
+        if (col < eo)                { kind = 0; net = &p.etaphi; o = col;            hoff = 0; }
+        else if (col < eo + lo)      { kind = 1; o = col - eo; }
+        else if (col < eo + lo + po) { kind = 0; net = &p.proxy;  o = col - eo - lo;  hoff = kMaxHid; }
+        else if (col < p.cond)       { kind = 2; }
+        else                         { kind = 0; net = &p.noisy;  o = col - p.cond;   hoff = 2 * kMaxHid; }
+        float w[kMaxHid];
+        float b2 = 0.f;
+        if (kind == 0) {
+#pragma unroll
+            for (int j = 0; j < kMaxHid; ++j) w[j] = j < net->hid ? __ldg(net->w2 + (size_t)o * net->hid + j) : 0.f;
+            b2 = __ldg(net->b2 + o);
+        }
+        float colsum = 0.f;
+        for (int tok = 0; tok < len; ++tok) {
+            float val;
+            if (kind == 0) {
+                float acc = b2;
+#pragma unroll
+                for (int j = 0; j < kMaxHid; ++j) acc = fmaf(w[j], s_hid[tok][hoff + j], acc);
+                val = leaky_relu(acc);
+            } else if (kind == 1) {
+                val = p.layer_out[((size_t)e * 3 + s_layer[tok]) * lo + o];
+            } else {
+                val = s_x[tok][3];
+            }
+            p.tok_feat[((size_t)r0 + tok) * p.ld + col] = val;
+            colsum += val;
+        }
+        if (col < p.cond) p.partial[(size_t)c * p.cond + col] = colsum;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// 3. context = cat[time_emb, masked mean of cond_feat] (models/flow_model.py:210-222) and
+//    SiLU(context), the shared input of every adaLN Linear (diffusion_transformer.py:27-28).
+//    Chunk partials are summed in a fixed order (deterministic, no atomics).
+// ------------------------------------------------------------------------------------
+struct ContextParams {
+    const float* temb; const float* partial;
+    const int* ev_chunk_start;      // [pass events + 1], pass-local chunk index
+    const int* cu_seqlens;          // global
+    float* ctx; float* silu_ctx;    // [B, ctx_dim]
+    int t_emb, cond, e0;
+};
+
+__global__ void __launch_bounds__(256) context_kernel(ContextParams p) {
+    const int el = blockIdx.x, e = p.e0 + el;
+    const int n = p.cu_seqlens[e + 1] - p.cu_seqlens[e];
+    const int c0 = p.ev_chunk_start[el], c1 = p.ev_chunk_start[el + 1];
+    const int width = p.t_emb + p.cond;
+    for (int c = threadIdx.x; c < width; c += blockDim.x) {
+        float v;
+        if (c < p.t_emb) {
+            v = p.temb[(size_t)e * p.t_emb + c];
+        } else {
+            float s = 0.f;
+            for (int ch = c0; ch < c1; ++ch) s += p.partial[(size_t)ch * p.cond + (c - p.t_emb)];
+            v = n > 0 ? s / (float)n : 0.f;
+        }
+        p.ctx[(size_t)e * width + c] = v;
+        p.silu_ctx[(size_t)e * width + c] = silu(v);
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// 4. generic fp32 GEMM  C[M,N] = epilogue(A[M,K] . W[N,K]^T)   ('highest' precision path
+//    and all small per-event contractions)
+// ------------------------------------------------------------------------------------
+template <typename OutT>
+__global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__ A, int lda,
+                                                       const float* __restrict__ W, int ldw,
+                                                       OutT* C, int ldc, int M, int N, int K, GemmEpilogue ep) {
+    constexpr int BM = 64, BN = 64, BK = 16;
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Ws[BK][BN + 4];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < K; k0 += BK) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = tid + i * 256, r = idx / BK, kk = idx % BK;
+            const int gk = k0 + kk;
+            const int gm = m0 + r, gn = n0 + r;
+            As[kk][r] = (gm < M && gk < K) ? A[(size_t)gm * lda + gk] : 0.f;
+            Ws[kk][r] = (gn < N && gk < K) ? __ldg(W + (size_t)gn * ldw + gk) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float4 b4 = *reinterpret_cast<const float4*>(&Ws[kk][tx * 4]);
+            const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int row = m0 + ty * 4 + i;
+        if (row >= M) continue;
+        const int ev = ep.row_event ? ep.row_event[row] : row;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int col = n0 + tx * 4 + j;
+            if (col >= N) continue;
+            float v = acc[i][j];
+            if (ep.bias) v += __ldg(ep.bias + col);
+            if (ep.row_bias) v += ep.row_bias[(size_t)ev * ep.ld_row_bias + col];
+            if (ep.act == 1) v = leaky_relu(v);
+            if (ep.resid) v = fmaf(ep.gate[(size_t)ev * ep.ld_gate + col], v, ep.resid[(size_t)row * ep.ld_resid + col]);
+            store_out(C + (size_t)row * ldc + col, v);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// 5. LayerNorm (+ affine) (+ adaLN modulate) (+ second, non-affine LayerNorm)
+//    one warp per row, row held in registers, two-pass statistics in fp32.
+//    modulate: diffusion_transformer.py:8-9;  second LN: the norm_layer in front of the
+//    layer MLP's first Linear (dense.py:62).
+// ------------------------------------------------------------------------------------
+struct LnModParams {
+    const float* x; int ldx; int M; int W;           // W % 32 == 0, W <= 512
+    const float* ln_w; const float* ln_b;            // null: no affine
+    const float* shift; const float* scale; int ld_mod;   // per event; null: no modulation
+    const int* row_event;
+    int second_ln;
+};
+
+template <typename OutT>
+__global__ void __launch_bounds__(256) ln_mod_kernel(LnModParams p, OutT* out, int ldo) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= p.M) return;
+    const int per = p.W >> 5;
+    float v[16];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+        if (j < per) { v[j] = p.x[(size_t)row * p.ldx + lane + 32 * j]; s += v[j]; }
+    s = warp_sum(s);
+    float mean = s / (float)p.W, q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+        if (j < per) { const float d = v[j] - mean; q = fmaf(d, d, q); }
+    q = warp_sum(q);
+    float rstd = 1.0f / sqrtf(q / (float)p.W + kLnEps);
+    const int ev = p.row_event ? p.row_event[row] : row;
+    s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+        if (j < per) {
+            const int col = lane + 32 * j;
+            float y = (v[j] - mean) * rstd;
+            if (p.ln_w) y = fmaf(y, __ldg(p.ln_w + col), __ldg(p.ln_b + col));
+            if (p.scale) y = fmaf(y, 1.f + p.scale[(size_t)ev * p.ld_mod + col], p.shift[(size_t)ev * p.ld_mod + col]);
+            v[j] = y; s += y;
+        }
+    if (p.second_ln) {
+        s = warp_sum(s);
+        mean = s / (float)p.W; q = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (j < per) { const float d = v[j] - mean; q = fmaf(d, d, q); }
+        q = warp_sum(q);
+        rstd = 1.0f / sqrtf(q / (float)p.W + kLnEps);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (j < per) v[j] = (v[j] - mean) * rstd;
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+        if (j < per) store_out(out + (size_t)row * ldo + lane + 32 * j, v[j]);
+}
+
+// ------------------------------------------------------------------------------------
+// 6. varlen attention, fp32, one thread per query, keys/values streamed through smem in
+//    tiles of 32; online softmax.  Padded keys are never loaded, padded queries never
+//    exist (models/attention.py:238-265 + models/utils.py:23-34 on real rows only;
+//    equal to the masked form up to reduction order).
+//    Handles self- and cross-attention: query rows and key rows come from separate
+//    (pointer, row stride) pairs and a per-work-item (q range, k range).
+// ------------------------------------------------------------------------------------
+struct AttnWork { int q_row, q_len, k_row, k_len; };
+
+template <int HD>
+__global__ void __launch_bounds__(128) attn_f32_kernel(const float* __restrict__ Q, int ldq,
+                                                       const float* __restrict__ Kp, const float* __restrict__ Vp, int ldkv,
+                                                       float* O, int ldo, const AttnWork* work, float inv_scale) {
+    constexpr int KT = 32;
+    __shared__ __align__(16) float Ks[KT][HD];
+    __shared__ __align__(16) float Vs[KT][HD];
+    const AttnWork w = work[blockIdx.x];
+    const int head = blockIdx.y;
+    const int tid = threadIdx.x;
+    const bool active = tid < w.q_len;
+    float q[HD], acc[HD];
+    if (active) {
+        const float* qp = Q + (size_t)(w.q_row + tid) * ldq + head * HD;
+#pragma unroll
+        for (int d = 0; d < HD; d += 4) {
+            const float4 t4 = *reinterpret_cast<const float4*>(qp + d);
+            q[d] = t4.x * inv_scale; q[d + 1] = t4.y * inv_scale; q[d + 2] = t4.z * inv_scale; q[d + 3] = t4.w * inv_scale;
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < HD; ++d) acc[d] = 0.f;
+    float m = -INFINITY, l = 0.f;
+    for (int k0 = 0; k0 < w.k_len; k0 += KT) {
+        const int kt = min(KT, w.k_len - k0);
+        __syncthreads();
+        for (int i = tid; i < kt * (HD / 4); i += blockDim.x) {
+            const int kk = i / (HD / 4), d4 = i % (HD / 4);
+            const size_t off = (size_t)(w.k_row + k0 + kk) * ldkv + head * HD + d4 * 4;
+            *reinterpret_cast<float4*>(&Ks[kk][d4 * 4]) = *reinterpret_cast<const float4*>(Kp + off);
+            *reinterpret_cast<float4*>(&Vs[kk][d4 * 4]) = *reinterpret_cast<const float4*>(Vp + off);
+        }
+        __syncthreads();
+        if (!active) continue;
+        float sc[KT];
+        float tmax = -INFINITY;
+#pragma unroll
+        for (int kk = 0; kk < KT; ++kk) {
+            float s = 0.f;
+            if (kk < kt) {
+#pragma unroll
+                for (int d = 0; d < HD; d += 4) {
+                    const float4 k4 = *reinterpret_cast<const float4*>(&Ks[kk][d]);
+                    s = fmaf(q[d], k4.x, s); s = fmaf(q[d + 1], k4.y, s);
+                    s = fmaf(q[d + 2], k4.z, s); s = fmaf(q[d + 3], k4.w, s);
+                }
+                tmax = fmaxf(tmax, s);
+            } else {
+                s = -INFINITY;
+            }
+            sc[kk] = s;
+        }
+        const float mnew = fmaxf(m, tmax);
+        const float corr = expf(m - mnew);          // m = -inf on the first tile -> 0
+        l *= corr;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) acc[d] *= corr;
+#pragma unroll
+        for (int kk = 0; kk < KT; ++kk) {
+            if (kk < kt) {
+                const float pw = expf(sc[kk] - mnew);
+                l += pw;
+#pragma unroll
+                for (int d = 0; d < HD; d += 4) {
+                    const float4 v4 = *reinterpret_cast<const float4*>(&Vs[kk][d]);
+                    acc[d] = fmaf(pw, v4.x, acc[d]); acc[d + 1] = fmaf(pw, v4.y, acc[d + 1]);
+                    acc[d + 2] = fmaf(pw, v4.z, acc[d + 2]); acc[d + 3] = fmaf(pw, v4.w, acc[d + 3]);
+                }
+            }
+        }
+        m = mnew;
+    }
+    if (active) {
+        const float inv = l > 0.f ? 1.f / l : 0.f;    // no keys: zero row, like masked_fill(0)
+        float* op = O + (size_t)(w.q_row + tid) * ldo + head * HD;
+#pragma unroll
+        for (int d = 0; d < HD; d += 4)
+            *reinterpret_cast<float4*>(op + d) = make_float4(acc[d] * inv, acc[d + 1] * inv, acc[d + 2] * inv, acc[d + 3] * inv);
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// 7. velocity head, part 1 (models/flow_model.py:241-245 + dense.py:62 of v_t_pred_net):
+//    hin[row] = LN_512( cat[ modulate(norm_v_t(cat[final_norm(x), cond_feat])), context ] )
+// ------------------------------------------------------------------------------------
+struct HeadPrepParams {
+    const float* x; int ldx;              // residual stream after the last DiT layer [Tp, h]
+    const float* tok_feat; int ldt;       // cond_feat = first `cond` columns
+    const float* fn_w; const float* fn_b; // transformer.final_norm
+    const float* nv_w; const float* nv_b; // norm_v_t
+    const float* shift; const float* scale; int ld_mod;   // v_t adaLN chunk(2): shift | scale
+    const float* ctx; int ctx_dim;
+    const int* row_event;
+    int M, h, cond;
+    float* final_tap;                     // optional [Tp, h]: final_norm(x)
+};
+
+template <typename OutT, int PH, int PC, int PX>     // per-lane counts: h/32, cond/32, ctx/32
+__global__ void __launch_bounds__(256) head_prep_kernel(HeadPrepParams p, OutT* hin, int ldh) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= p.M) return;
+    constexpr int PV = PH + PC, PT = PV + PX;
+    const int ev = p.row_event[row];
+    float v[PT];                         // [0,PH) final_norm part, [PH,PV) cond_feat, [PV,PT) context
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int j = 0; j < PH; ++j) { v[j] = p.x[(size_t)row * p.ldx + lane + 32 * j]; s += v[j]; }
+    s = warp_sum(s);
+    float mean = s / (float)p.h;
+#pragma unroll
+    for (int j = 0; j < PH; ++j) { const float d = v[j] - mean; q = fmaf(d, d, q); }
+    q = warp_sum(q);
+    float rstd = 1.0f / sqrtf(q / (float)p.h + kLnEps);
+    s = 0.f;
+#pragma unroll
+    for (int j = 0; j < PH; ++j) {
+        const int col = lane + 32 * j;
+        v[j] = fmaf((v[j] - mean) * rstd, __ldg(p.fn_w + col), __ldg(p.fn_b + col));
+        if (p.final_tap) p.final_tap[(size_t)row * p.h + col] = v[j];
+        s += v[j];
+    }
+#pragma unroll
+    for (int j = 0; j < PC; ++j) { v[PH + j] = p.tok_feat[(size_t)row * p.ldt + lane + 32 * j]; s += v[PH + j]; }
+    // norm_v_t over h + cond, affine, then modulate
+    const int vin = p.h + p.cond;
+    s = warp_sum(s);
+    mean = s / (float)vin; q = 0.f;
+#pragma unroll
+    for (int j = 0; j < PV; ++j) { const float d = v[j] - mean; q = fmaf(d, d, q); }
+    q = warp_sum(q);
+    rstd = 1.0f / sqrtf(q / (float)vin + kLnEps);
+    s = 0.f;
+#pragma unroll
+    for (int j = 0; j < PV; ++j) {
+        const int col = j < PH ? lane + 32 * j : p.h + lane + 32 * (j - PH);
+        float y = fmaf((v[j] - mean) * rstd, __ldg(p.nv_w + col), __ldg(p.nv_b + col));
+        y = fmaf(y, 1.f + p.scale[(size_t)ev * p.ld_mod + col], p.shift[(size_t)ev * p.ld_mod + col]);
+        v[j] = y; s += y;
+    }
+#pragma unroll
+    for (int j = 0; j < PX; ++j) { v[PV + j] = p.ctx[(size_t)ev * p.ctx_dim + lane + 32 * j]; s += v[PV + j]; }
+    // LayerNorm (no affine) over v_in + ctx
+    const int tot = vin + p.ctx_dim;
+    s = warp_sum(s);
+    mean = s / (float)tot; q = 0.f;
+#pragma unroll
+    for (int j = 0; j < PT; ++j) { const float d = v[j] - mean; q = fmaf(d, d, q); }
+    q = warp_sum(q);
+    rstd = 1.0f / sqrtf(q / (float)tot + kLnEps);
+#pragma unroll
+    for (int j = 0; j < PT; ++j) {
+        int col;
+        if (j < PH) col = lane + 32 * j;
+        else if (j < PV) col = p.h + lane + 32 * (j - PH);
+        else col = vin + lane + 32 * (j - PV);
+        store_out(hin + (size_t)row * ldh + col, (v[j] - mean) * rstd);
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// 8. velocity head, part 2 + fused ODE update:
+//    h1 -> LN -> Linear -> LeakyReLU -> LN -> Linear -> LeakyReLU -> [LN] -> Linear -> v
+//    (tail of v_t_pred_net, models/dense.py:49-78), then out = base + coef * v  (the
+//    euler / midpoint stage update of torchdiffeq's fixed-grid solvers).
+//    One warp per row; weights transposed in shared memory (bank-conflict free).
+// ------------------------------------------------------------------------------------
+struct HeadTailParams {
+    const float* h1; int ldh; int M;
+    const float* w2; const float* b2;     // [H2, H1]
+    const float* w3; const float* b3;     // [H3, H2]
+    const float* w4; const float* b4;     // [1, H3]
+    int H1, H2, H3, final_ln;
+    const StageParams* sp; const int* stage_idx;     // null sp: use fixed pointers below
+    float* vout_fixed;
+};
+
+constexpr int kHeadWarps = 8;
+
+__global__ void __launch_bounds__(kHeadWarps * 32) head_tail_kernel(HeadTailParams p) {
+    extern __shared__ float smem[];
+    float* w2t = smem;                               // [H1][H2]
+    float* w3t = w2t + p.H1 * p.H2;                  // [H2][H3]
+    float* w4s = w3t + p.H2 * p.H3;                  // [H3]
+    float* b2s = w4s + p.H3;
+    float* b3s = b2s + p.H2;
+    float* buf = b3s + p.H3;                         // [warps][H1]
+    for (int i = threadIdx.x; i < p.H1 * p.H2; i += blockDim.x) { const int o = i / p.H1, k = i % p.H1; w2t[k * p.H2 + o] = __ldg(p.w2 + i); }
+    for (int i = threadIdx.x; i < p.H2 * p.H3; i += blockDim.x) { const int o = i / p.H2, k = i % p.H2; w3t[k * p.H3 + o] = __ldg(p.w3 + i); }
+    for (int i = threadIdx.x; i < p.H3; i += blockDim.x) { w4s[i] = __ldg(p.w4 + i); b3s[i] = __ldg(p.b3 + i); }
+    for (int i = threadIdx.x; i < p.H2; i += blockDim.x) b2s[i] = __ldg(p.b2 + i);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* my = buf + warp * p.H1;
+    const int n1 = p.H1 >> 5, n2 = p.H2 >> 5, n3 = p.H3 >> 5;
+    StageParams st;
+    if (p.sp) st = p.sp[*p.stage_idx];
+    else { st.out = nullptr; st.base = nullptr; st.coef = 0.f; st.vout = p.vout_fixed; }
+    const float b4 = __ldg(p.b4);
+    for (int row = blockIdx.x * kHeadWarps + warp; row < p.M; row += gridDim.x * kHeadWarps) {
+        float a[8];
+        float s = 0.f, q = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (j < n1) { a[j] = p.h1[(size_t)row * p.ldh + lane + 32 * j]; s += a[j]; }
+        s = warp_sum(s);
+        float mean = s / (float)p.H1;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (j < n1) { const float d = a[j] - mean; q = fmaf(d, d, q); }
+        q = warp_sum(q);
+        float rstd = 1.0f / sqrtf(q / (float)p.H1 + kLnEps);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (j < n1) my[lane + 32 * j] = (a[j] - mean) * rstd;
+        __syncwarp();
+        // Linear H1 -> H2, LeakyReLU
+        float o2[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) o2[r] = r < n2 ? b2s[lane + 32 * r] : 0.f;
+        for (int k = 0; k < p.H1; ++k) {
+            const float x = my[k];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) if (r < n2) o2[r] = fmaf(w2t[k * p.H2 + lane + 32 * r], x, o2[r]);
+        }
+        s = 0.f; q = 0.f;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) if (r < n2) { o2[r] = leaky_relu(o2[r]); s += o2[r]; }
+        s = warp_sum(s);
+        mean = s / (float)p.H2;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) if (r < n2) { const float d = o2[r] - mean; q = fmaf(d, d, q); }
+        q = warp_sum(q);
+        rstd = 1.0f / sqrtf(q / (float)p.H2 + kLnEps);
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 4; ++r) if (r < n2) my[lane + 32 * r] = (o2[r] - mean) * rstd;
+        __syncwarp();
+        // Linear H2 -> H3, LeakyReLU
+        float o3[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) o3[r] = r < n3 ? b3s[lane + 32 * r] : 0.f;
+        for (int k = 0; k < p.H2; ++k) {
+            const float x = my[k];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) if (r < n3) o3[r] = fmaf(w3t[k * p.H3 + lane + 32 * r], x, o3[r]);
+        }
+        s = 0.f; q = 0.f;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) if (r < n3) { o3[r] = leaky_relu(o3[r]); s += o3[r]; }
+        if (p.final_ln) {
+            s = warp_sum(s);
+            mean = s / (float)p.H3;
+#pragma unroll
+            for (int r = 0; r < 2; ++r) if (r < n3) { const float d = o3[r] - mean; q = fmaf(d, d, q); }
+            q = warp_sum(q);
+            rstd = 1.0f / sqrtf(q / (float)p.H3 + kLnEps);
+#pragma unroll
+            for (int r = 0; r < 2; ++r) if (r < n3) o3[r] = (o3[r] - mean) * rstd;
+        }
+        float v = 0.f;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) if (r < n3) v = fmaf(w4s[lane + 32 * r], o3[r], v);
+        v = warp_sum(v) + b4;
+        __syncwarp();
+        if (lane == 0) {
+            if (st.vout) st.vout[row] = v;
+            if (st.out) st.out[row] = fmaf(st.coef, v, st.base[row]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// 9. small utilities
+// ------------------------------------------------------------------------------------
+// row -> global event id, from cu_seqlens (one block per event)
+__global__ void row_event_kernel(const int* cu_seqlens, int* row_event, int n_events) {
+    const int e = blockIdx.x;
+    if (e >= n_events) return;
+    for (int r = cu_seqlens[e] + threadIdx.x; r < cu_seqlens[e + 1]; r += blockDim.x) row_event[r] = e;
+}
+
+// advances the device-side stage counter (last node of a captured evaluation graph)
+__global__ void bump_stage_kernel(int* stage_idx) { if (threadIdx.x == 0 && blockIdx.x == 0) ++*stage_idx; }
+
+// out = base + sum_i c[i] * k[i]   (RK stage inputs / solutions / error estimates)
+struct CombineParams { const float* base; const float* k[7]; float c[7]; int nk; float* out; size_t n; };
+__global__ void combine_kernel(CombineParams p) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < p.n; i += (size_t)gridDim.x * blockDim.x) {
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) if (j < p.nk) acc = fmaf(p.c[j], p.k[j][i], acc);
+        p.out[i] = p.base ? p.base[i] + acc : acc;
+    }
+}
+
+}  // namespace srhep
