@@ -1,0 +1,75 @@
+"""ctypes binding of include/srhep.h.  No torch types cross this boundary: device pointers
+travel as integers (``tensor.data_ptr()``), streams as ``cudaStream_t`` handles."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+from .config import SrDimsC
+
+_LIB: Optional[C.CDLL] = None
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsrhep.so")
+
+PREC_FP32, PREC_BF16 = 0, 1
+METHODS = {"euler": 0, "midpoint": 1, "rk4": 2, "dopri5": 3}
+
+# every symbol include/srhep.h declares
+EXPORTS = (
+    "srhep_version", "srhep_weight_count", "srhep_create", "srhep_destroy", "srhep_last_error",
+    "srhep_set_pass_tokens", "srhep_set_use_graph", "srhep_bind_events", "srhep_velocity",
+    "srhep_sample", "srhep_sample_dopri5", "srhep_set_debug", "srhep_get_tap", "srhep_launch_count",
+)
+
+
+class SrhepCond(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("eta", "cosphi", "sinphi", "e_proxy", "layer")]
+
+
+def load() -> C.CDLL:
+    """Loads libsrhep.so.  There is no fallback: a missing library is an error."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.isfile(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m superresolutionhep_b200.build` "
+            "(nvcc, sm_100a). This package has no CPU or PyTorch fallback path.")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, u64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_float
+    lib.srhep_version.restype = C.c_char_p
+    lib.srhep_version.argtypes = []
+    lib.srhep_weight_count.restype = C.c_size_t
+    lib.srhep_weight_count.argtypes = [C.POINTER(SrDimsC)]
+    lib.srhep_create.restype = C.c_int
+    lib.srhep_create.argtypes = [C.c_int, C.POINTER(SrDimsC), vp, C.c_size_t, C.c_int, C.POINTER(vp)]
+    lib.srhep_destroy.restype = C.c_int
+    lib.srhep_destroy.argtypes = [vp]
+    lib.srhep_last_error.restype = C.c_char_p
+    lib.srhep_last_error.argtypes = [vp]
+    lib.srhep_set_pass_tokens.restype = C.c_int
+    lib.srhep_set_pass_tokens.argtypes = [vp, i64]
+    lib.srhep_set_use_graph.restype = C.c_int
+    lib.srhep_set_use_graph.argtypes = [vp, C.c_int]
+    lib.srhep_set_debug.restype = C.c_int
+    lib.srhep_set_debug.argtypes = [vp, C.c_int]
+    lib.srhep_bind_events.restype = C.c_int
+    lib.srhep_bind_events.argtypes = [vp, C.POINTER(SrhepCond), vp, i32, vp]
+    lib.srhep_velocity.restype = C.c_int
+    lib.srhep_velocity.argtypes = [vp, vp, vp, vp, vp]
+    lib.srhep_sample.restype = C.c_int
+    lib.srhep_sample.argtypes = [vp, vp, vp, i32, i32, i32, vp, C.POINTER(i32), vp]
+    lib.srhep_sample_dopri5.restype = C.c_int
+    lib.srhep_sample_dopri5.argtypes = [vp, vp, vp, i32, f32, f32, i32, vp, C.POINTER(i32), vp]
+    lib.srhep_get_tap.restype = C.c_int
+    lib.srhep_get_tap.argtypes = [vp, C.c_char_p, vp, C.c_size_t, vp]
+    lib.srhep_launch_count.restype = u64
+    lib.srhep_launch_count.argtypes = [vp]
+    _LIB = lib
+    return lib
+
+
+def check(lib: C.CDLL, handle, rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib.srhep_last_error(handle)
+        raise RuntimeError(f"{what} failed (code {rc}): {msg.decode() if msg else '?'}")

@@ -36,6 +36,18 @@ struct StageParams {
     float*       vout;    // raw velocity (may be null)
 };
 
+// How a kernel finds the stage it is working for.  Graph replay: sp[*idx] (the captured
+// launch arguments never change, the device-side counter does).  Direct launch: `fixed`.
+// t_event (optional, indexed by global event id) overrides the shared stage time -- the
+// FlowModel.forward(batch, x, time_step) entry point takes one time per event.
+struct StageRef {
+    const StageParams* sp      = nullptr;
+    const int*         idx     = nullptr;
+    StageParams        fixed   = {};
+    const float*       t_event = nullptr;
+};
+__device__ __forceinline__ StageParams load_stage(const StageRef& r) { return r.sp ? r.sp[*r.idx] : r.fixed; }
+
 // Epilogue description shared by the fp32 and the bf16 GEMM kernels:
 //   val = act(acc + bias[n] + row_bias[event(row)][n])
 //   C   = resid ? resid[row][n] + gate[event(row)][n] * val : val

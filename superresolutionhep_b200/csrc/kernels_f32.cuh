@@ -62,8 +62,7 @@ struct EventPrepParams {
     float* ev_a;        // [B, 3, kMaxHid]   etaphi / proxy / noisy
     float* ev_stats;    // [B, 2]            mean(temb), sum (temb - mean)^2
     float* layer_out;   // [B, 3, layer.out]
-    const float* t_event;
-    const StageParams* sp; const int* stage_idx;
+    StageRef stage;
     int e0;
 };
 
@@ -76,7 +75,7 @@ __global__ void __launch_bounds__(128) event_prep_kernel(EventPrepParams p) {
     __shared__ float s_stat[2];
     const int tid = threadIdx.x;
     const int e = p.e0 + blockIdx.x;
-    const float t = p.t_event ? p.t_event[e] : p.sp[*p.stage_idx].t;
+    const float t = p.stage.t_event ? p.stage.t_event[e] : load_stage(p.stage).t;
 
     for (int i = tid; i < p.half; i += blockDim.x) {
         const float a = t * __ldg(p.freqs + i);
@@ -152,8 +151,9 @@ struct EmbedTokParams {
     EmbedNetDev etaphi, proxy, noisy;
     int layer_out_dim, t_emb, cond, ncol;
     const float *eta, *cosphi, *sinphi, *e_proxy; const int* layer;
-    const float* x_in_fixed;
-    const StageParams* sp; const int* stage_idx;
+    StageRef stage;                      // x_in: pass-local rows
+    int row0;                            // first global row of the pass
+    int chunk0;                          // first global chunk of the pass
     const float* ev_a; const float* ev_stats; const float* layer_out;
     const int *chunk_event, *chunk_row, *chunk_len;
     float* tok_feat; int ld;
@@ -166,9 +166,9 @@ __global__ void __launch_bounds__(192) embed_tokens_kernel(EmbedTokParams p) {
     __shared__ float s_mu[kChunk][3], s_rs[kChunk][3];
     __shared__ float s_hid[kChunk][3 * kMaxHid + 1];
     const int tid = threadIdx.x;
-    const int c = blockIdx.x;
+    const int c = p.chunk0 + blockIdx.x;
     const int e = p.chunk_event[c], r0 = p.chunk_row[c], len = p.chunk_len[c];
-    const float* x_in = p.x_in_fixed ? p.x_in_fixed : p.sp[*p.stage_idx].x_in;
+    const float* x_in = load_stage(p.stage).x_in;
 
     for (int i = tid; i < len * 6; i += blockDim.x) {
         const int tok = i / 6, f = i % 6;
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(192) embed_tokens_kernel(EmbedTokParams p) {
         else if (f == 1) s_x[tok][1] = p.cosphi[r];
         else if (f == 2) s_x[tok][2] = p.sinphi[r];
         else if (f == 3) s_x[tok][3] = p.e_proxy[r];
-        else if (f == 4) s_x[tok][4] = x_in[r];
+        else if (f == 4) s_x[tok][4] = x_in[r - p.row0];
         else s_layer[tok] = p.layer[r];
     }
     __syncthreads();
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(192) embed_tokens_kernel(EmbedTokParams p) {
             } else {
                 val = s_x[tok][3];
             }
-            p.tok_feat[((size_t)r0 + tok) * p.ld + col] = val;
+            p.tok_feat[((size_t)(r0 - p.row0) + tok) * p.ld + col] = val;
             colsum += val;
         }
         if (col < p.cond) p.partial[(size_t)c * p.cond + col] = colsum;
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(192) embed_tokens_kernel(EmbedTokParams p) {
 // ------------------------------------------------------------------------------------
 struct ContextParams {
     const float* temb; const float* partial;
-    const int* ev_chunk_start;      // [pass events + 1], pass-local chunk index
+    const int* ev_chunk_start;      // [B + 1], global chunk index
     const int* cu_seqlens;          // global
     float* ctx; float* silu_ctx;    // [B, ctx_dim]
     int t_emb, cond, e0;
@@ -279,7 +279,7 @@ struct ContextParams {
 __global__ void __launch_bounds__(256) context_kernel(ContextParams p) {
     const int el = blockIdx.x, e = p.e0 + el;
     const int n = p.cu_seqlens[e + 1] - p.cu_seqlens[e];
-    const int c0 = p.ev_chunk_start[el], c1 = p.ev_chunk_start[el + 1];
+    const int c0 = p.ev_chunk_start[e], c1 = p.ev_chunk_start[e + 1];
     const int width = p.t_emb + p.cond;
     for (int c = threadIdx.x; c < width; c += blockDim.x) {
         float v;
@@ -597,8 +597,7 @@ struct HeadTailParams {
     const float* w3; const float* b3;     // [H3, H2]
     const float* w4; const float* b4;     // [1, H3]
     int H1, H2, H3, final_ln;
-    const StageParams* sp; const int* stage_idx;     // null sp: use fixed pointers below
-    float* vout_fixed;
+    StageRef stage;                       // out / base / vout: pass-local rows
 };
 
 constexpr int kHeadWarps = 8;
@@ -619,9 +618,7 @@ __global__ void __launch_bounds__(kHeadWarps * 32) head_tail_kernel(HeadTailPara
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* my = buf + warp * p.H1;
     const int n1 = p.H1 >> 5, n2 = p.H2 >> 5, n3 = p.H3 >> 5;
-    StageParams st;
-    if (p.sp) st = p.sp[*p.stage_idx];
-    else { st.out = nullptr; st.base = nullptr; st.coef = 0.f; st.vout = p.vout_fixed; }
+    const StageParams st = load_stage(p.stage);
     const float b4 = __ldg(p.b4);
     for (int row = blockIdx.x * kHeadWarps + warp; row < p.M; row += gridDim.x * kHeadWarps) {
         float a[8];
@@ -714,6 +711,34 @@ __global__ void combine_kernel(CombineParams p) {
 #pragma unroll
         for (int j = 0; j < 7; ++j) if (j < p.nk) acc = fmaf(p.c[j], p.k[j][i], acc);
         p.out[i] = p.base ? p.base[i] + acc : acc;
+    }
+}
+
+
+// sum_i ( (a[i] - a2[i]) / (atol + rtol * max(|s1[i]|, |s2[i]|)) )^2  accumulated in double
+// (the rms norms of torchdiffeq's dopri5 step controller, over real cells only)
+__global__ void __launch_bounds__(256) scaled_sumsq_kernel(const float* __restrict__ a, const float* __restrict__ a2,
+                                                           const float* __restrict__ s1, const float* __restrict__ s2,
+                                                           float atol, float rtol, size_t n, double* out) {
+    double acc = 0.0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float v = a[i];
+        if (a2) v -= a2[i];
+        float sc = fabsf(s1[i]);
+        if (s2) sc = fmaxf(sc, fabsf(s2[i]));
+        const float q = v / (atol + rtol * sc);
+        acc += (double)q * (double)q;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    __shared__ double sred[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) sred[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sred[w];
+        atomicAdd(out, t);
     }
 }
 

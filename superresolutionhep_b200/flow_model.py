@@ -1,0 +1,268 @@
+"""Drop-in for the reference's ``models/flow_model.py:FlowModel`` on the inference path.
+
+Same constructor argument (the YAML ``flow_model`` block), same ``state_dict()`` keys and
+shapes, same ``forward(batch, noisy_input, time_step)`` and
+``generate_samples(batch, n_steps, method, ret_seq)`` signatures and output tensors
+(models/flow_model.py:167, :303).  Underneath, the padded ``(B, Nmax, 1)`` batch is packed
+to real cells only (``q_mask`` -> ``cu_seqlens``) and handed to the C-ABI library
+(include/srhep.h); nothing here computes the network in PyTorch.
+
+Differences a caller can observe, all in padded slots (which the reference's callers mask
+out, inference.py:199-214): ``forward`` returns 0 there (the reference returns finite
+garbage) and ``generate_samples`` leaves the initial noise there.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Optional
+
+import torch
+from torch import nn
+
+from . import _lib
+from .config import SrDims
+
+_PREC_ENV = "SRHEP_PRECISION"
+
+
+class _Params(nn.Module):
+    """Bare container: gives nested ``a.b.1.weight`` state_dict keys without computing."""
+
+
+def _register(root: nn.Module, dotted: str, shape) -> None:
+    *mods, leaf = dotted.split(".")
+    m = root
+    for name in mods:
+        if name not in m._modules:
+            m.add_module(name, _Params())
+        m = m._modules[name]
+    m.register_parameter(leaf, nn.Parameter(torch.zeros(shape), requires_grad=False))
+
+
+def _resolve_precision(precision: Optional[str]) -> int:
+    """'fp32' | 'bf16' | None.  None follows the reference's ``-p/--precision`` switch
+    (inference.py:330 -> torch.set_float32_matmul_precision): 'highest' keeps every
+    contraction in fp32, 'high' / 'medium' allow the bf16 tcgen05 path."""
+    p = precision or os.environ.get(_PREC_ENV)
+    if p is None:
+        p = "fp32" if torch.get_float32_matmul_precision() == "highest" else "bf16"
+    p = p.lower()
+    if p in ("fp32", "highest", "float32"):
+        return _lib.PREC_FP32
+    if p in ("bf16", "bfloat16", "high", "medium"):
+        return _lib.PREC_BF16
+    raise ValueError(f"unknown precision {precision!r}")
+
+
+class PackedEvents:
+    """Real cells of a padded ``collate_graphs`` batch (dataset.py:341-349), compacted."""
+
+    def __init__(self, batch: Dict[str, torch.Tensor], device: torch.device):
+        q_mask = batch["q_mask"]
+        if q_mask.dtype != torch.bool:
+            q_mask = q_mask.bool()
+        self.mask = q_mask.to(device)
+        self.shape = tuple(batch["e_proxy"].shape)                     # (B, Nmax, 1)
+        lens = self.mask.sum(1, dtype=torch.int32)
+        cu = torch.zeros(self.mask.shape[0] + 1, dtype=torch.int32)
+        cu[1:] = torch.cumsum(lens.cpu(), 0, dtype=torch.int32)
+        self.cu_host = cu.contiguous()
+        self.n_events = self.mask.shape[0]
+        self.n_cells = int(cu[-1])
+
+        def take(key, dtype):
+            v = batch[key].to(device)
+            return v.reshape(self.mask.shape)[self.mask].to(dtype).contiguous()
+
+        self.eta = take("eta", torch.float32)
+        self.cosphi = take("cosphi", torch.float32)
+        self.sinphi = take("sinphi", torch.float32)
+        self.e_proxy = take("e_proxy", torch.float32)
+        self.layer = take("layer", torch.int32)
+
+    def cond_struct(self) -> _lib.SrhepCond:
+        return _lib.SrhepCond(self.eta.data_ptr(), self.cosphi.data_ptr(), self.sinphi.data_ptr(),
+                              self.e_proxy.data_ptr(), self.layer.data_ptr())
+
+    def pack(self, x: torch.Tensor) -> torch.Tensor:
+        return x.to(self.mask.device).reshape(self.mask.shape)[self.mask].float().contiguous()
+
+    def unpack(self, packed: torch.Tensor, fill: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """(..., T) -> (..., B, Nmax, 1)."""
+        lead = packed.shape[:-1]
+        if fill is None:
+            out = packed.new_zeros(*lead, *self.mask.shape)
+        else:
+            out = fill.to(packed.device).reshape(self.mask.shape).expand(*lead, *self.mask.shape).clone()
+        out[..., self.mask] = packed
+        return out.unsqueeze(-1)
+
+
+class FlowModel(nn.Module):
+    def __init__(self, model_config: dict, precision: Optional[str] = None):
+        super().__init__()
+        self.model_config = model_config
+        self.dims = SrDims.from_config(model_config)
+        self.n_steps = self.dims.n_steps                                # flow_model.py:35
+        self.sigma_min = model_config.get("sigma_min", 0.0)
+        for name, shape in self.dims.param_shapes().items():
+            _register(self, name, shape)
+        self._precision_req = precision
+        self._handle = None
+        self._handle_key = None
+        self._bound: Optional[PackedEvents] = None
+        self._bound_key = None
+        self.pass_tokens = 0            # 0 = library default
+        self.use_graph = True
+        self.last_stats: dict = {}
+
+    # ------------------------------------------------------------------ handle management
+    def _weights_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def _device(self) -> torch.device:
+        return next(self.parameters()).device
+
+    def _ensure_handle(self):
+        dev = self._device()
+        if dev.type != "cuda":
+            raise RuntimeError("superresolutionhep_b200.FlowModel runs on CUDA (sm_100a) only; "
+                               "call .cuda() first -- there is no CPU path")
+        prec = _resolve_precision(self._precision_req)
+        key = (dev.index if dev.index is not None else torch.cuda.current_device(), prec, self._weights_key())
+        if self._handle is not None and key == self._handle_key:
+            return self._handle
+        self.release()
+        lib = _lib.load()
+        sd = self.state_dict()
+        half = self.dims.freq_dim // 2
+        # TimestepEmbedder frequencies exactly as models/utils.py:152-154 computes them
+        import math
+        freqs = torch.exp(-math.log(10000) * torch.arange(start=0, end=half, dtype=torch.float32) / half)
+        blob = torch.cat([sd[k].detach().float().cpu().reshape(-1) for k in self.dims.param_order()] + [freqs]).contiguous()
+        dc = self.dims.to_c()
+        need = lib.srhep_weight_count(C.byref(dc))
+        if need != blob.numel():
+            raise RuntimeError(f"weight blob mismatch: {blob.numel()} floats vs {need} expected")
+        h = C.c_void_p()
+        rc = lib.srhep_create(key[0], C.byref(dc), blob.data_ptr(), blob.numel(), prec, C.byref(h))
+        _lib.check(lib, None, rc, "srhep_create")
+        self._handle, self._handle_key = h, key
+        self._bound = None
+        self._bound_key = None
+        return h
+
+    def release(self):
+        if self._handle is not None:
+            _lib.load().srhep_destroy(self._handle)
+        self._handle = None
+        self._handle_key = None
+        self._bound = None
+        self._bound_key = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self) -> int:
+        return int(_lib.load().srhep_launch_count(self._handle)) if self._handle is not None else 0
+
+    # ------------------------------------------------------------------ binding
+    def _bind(self, batch) -> PackedEvents:
+        h = self._ensure_handle()
+        lib = _lib.load()
+        key = tuple((k, batch[k].data_ptr(), batch[k]._version, tuple(batch[k].shape))
+                    for k in ("eta", "cosphi", "sinphi", "e_proxy", "layer", "q_mask")) + (self.pass_tokens, self.use_graph)
+        if self._bound is not None and key == self._bound_key:
+            return self._bound
+        dev = self._device()
+        ev = PackedEvents(batch, dev)
+        _lib.check(lib, h, lib.srhep_set_pass_tokens(h, int(self.pass_tokens)), "srhep_set_pass_tokens")
+        _lib.check(lib, h, lib.srhep_set_use_graph(h, 1 if self.use_graph else 0), "srhep_set_use_graph")
+        cond = ev.cond_struct()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = lib.srhep_bind_events(h, C.byref(cond), ev.cu_host.data_ptr(), ev.n_events, stream)
+        _lib.check(lib, h, rc, "srhep_bind_events")
+        self._bound, self._bound_key = ev, key
+        return ev
+
+    # ------------------------------------------------------------------ reference surface
+    @torch.no_grad()
+    def forward(self, batch, noisy_input, time_step, verbose=False):
+        """models/flow_model.py:167 -- v_t of shape (B, Nmax, 1)."""
+        ev = self._bind(batch)
+        lib, h = _lib.load(), self._handle
+        dev = self._device()
+        x = ev.pack(noisy_input)
+        t = time_step.to(dev).float().reshape(-1).contiguous()
+        if t.numel() != ev.n_events:
+            raise ValueError(f"time_step must have one entry per event ({ev.n_events}), got {t.numel()}")
+        v = torch.empty_like(x)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib, h, lib.srhep_velocity(h, x.data_ptr(), t.data_ptr(), v.data_ptr(), stream), "srhep_velocity")
+        return ev.unpack(v)
+
+    @torch.no_grad()
+    def generate_samples(self, batch, n_steps=None, method="dopri5", ret_seq=False, x0=None,
+                         atol: float = 1e-4, rtol: float = 1e-4):
+        """models/flow_model.py:302-329.  ``x0`` (optional, (B, Nmax, 1)) replaces the
+        ``torch.randn_like(e_proxy)`` draw of line 319, e.g. for sharded or seeded runs."""
+        if n_steps is None:
+            n_steps = self.n_steps
+        if method not in _lib.METHODS:
+            raise ValueError(f"unsupported method {method!r}; available: {sorted(_lib.METHODS)}")
+        ev = self._bind(batch)
+        lib, h = _lib.load(), self._handle
+        dev = self._device()
+        proxy_e = batch["e_proxy"]
+        if x0 is None:
+            x0 = torch.randn_like(proxy_e, device=proxy_e.device)       # same call as the reference
+        x0p = ev.pack(x0)
+        tgrid = torch.linspace(0, 1, n_steps).float().contiguous()      # fp32 grid, as torchdiffeq sees it
+        T = ev.n_cells
+        out = torch.empty((n_steps, T) if ret_seq else (T,), dtype=torch.float32, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        if method == "dopri5":
+            stats = (C.c_int32 * 3)()
+            rc = lib.srhep_sample_dopri5(h, x0p.data_ptr(), tgrid.data_ptr(), n_steps, atol, rtol, 1 if ret_seq else 0,
+                                         out.data_ptr(), stats, stream)
+            _lib.check(lib, h, rc, "srhep_sample_dopri5")
+            self.last_stats = dict(nfe=stats[0], accepted=stats[1], rejected=stats[2])
+        else:
+            nfe = C.c_int32(0)
+            rc = lib.srhep_sample(h, x0p.data_ptr(), tgrid.data_ptr(), n_steps, _lib.METHODS[method], 1 if ret_seq else 0,
+                                  out.data_ptr(), C.byref(nfe), stream)
+            _lib.check(lib, h, rc, "srhep_sample")
+            self.last_stats = dict(nfe=nfe.value)
+        return ev.unpack(out, fill=x0.float())
+
+    # ------------------------------------------------------------------ parity hooks
+    def debug_taps(self, batch, noisy_input, time_step, names):
+        """Per-stage activations of one forward (packed rows), for the parity tests."""
+        h = self._ensure_handle()
+        lib = _lib.load()
+        _lib.check(lib, h, lib.srhep_set_debug(h, 1), "srhep_set_debug")
+        self._bound = None
+        try:
+            ev = self._bind(batch)
+            v = self.forward(batch, noisy_input, time_step)
+            dev = self._device()
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            d = self.dims
+            sizes = {"time_emb": (ev.n_events, d.t_emb), "context": (ev.n_events, d.ctx),
+                     "tok_feat": (ev.n_cells, d.cond + d.noisy_out), "feat_0": (ev.n_cells, d.h_dim),
+                     "transformer_out": (ev.n_cells, d.h_dim), "mod": (ev.n_events, d.mod_width)}
+            out = {"v_t": v}
+            for n in names:
+                shape = sizes.get(n, (ev.n_cells, d.h_dim))
+                t = torch.empty(shape, dtype=torch.float32, device=dev)
+                _lib.check(lib, h, lib.srhep_get_tap(h, n.encode(), t.data_ptr(), t.numel(), stream), f"srhep_get_tap({n})")
+                out[n] = t
+            return out, ev
+        finally:
+            lib.srhep_set_debug(h, 0)
+            self._bound = None
