@@ -122,6 +122,24 @@ int srhep_sample_dopri5(SrhepHandle* h, const float* x0_dev, const float* t_grid
 int srhep_set_debug(SrhepHandle* h, int enable);
 int srhep_get_tap(SrhepHandle* h, const char* name, float* out_dev, size_t n_floats, void* stream);
 
+/* Measurement hook (bench.py's roofline leg): one srhep_velocity-equivalent evaluation at a
+ * single time t over all passes, launched directly (no graph) with a CUDA event after every
+ * kernel on `stream`; returns the device time and launch count per kernel category.
+ * Synchronises the stream.  ms_by_cat / launches_by_cat: host arrays of SRHEP_NCAT. */
+#define SRHEP_CAT_EMBED 0   /* timestep embedding, cell embedding nets, masked mean    */
+#define SRHEP_CAT_ADALN 1   /* per-event GEMMs: all adaLN Linears, feat_0 context part */
+#define SRHEP_CAT_FEAT0 2   /* feat_0_mlp token GEMM                                    */
+#define SRHEP_CAT_LN    3   /* LayerNorm + adaLN modulate                               */
+#define SRHEP_CAT_QKV   4   /* q|k|v projection GEMM                                    */
+#define SRHEP_CAT_ATTN  5   /* varlen attention                                         */
+#define SRHEP_CAT_OUT   6   /* attention output projection + gate + residual            */
+#define SRHEP_CAT_MLP1  7   /* layer MLP first Linear + LeakyReLU                       */
+#define SRHEP_CAT_MLP2  8   /* layer MLP second Linear + LeakyReLU + gate + residual    */
+#define SRHEP_CAT_HEAD  9   /* velocity head + ODE update                               */
+#define SRHEP_NCAT     10
+int srhep_profile(SrhepHandle* h, const float* x_dev, float t, float* v_dev, float* ms_by_cat,
+                  int32_t* launches_by_cat, void* stream);
+
 /* Kernels launched by this handle since creation (bench.py's gpu_launches claim). */
 uint64_t srhep_launch_count(const SrhepHandle* h);
 

@@ -13,12 +13,14 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsrhep.so
 
 PREC_FP32, PREC_BF16 = 0, 1
 METHODS = {"euler": 0, "midpoint": 1, "rk4": 2, "dopri5": 3}
+CATEGORIES = ("embed", "adaln", "feat0", "ln", "qkv", "attn", "out", "mlp1", "mlp2", "head")
 
 # every symbol include/srhep.h declares
 EXPORTS = (
     "srhep_version", "srhep_weight_count", "srhep_create", "srhep_destroy", "srhep_last_error",
     "srhep_set_pass_tokens", "srhep_set_use_graph", "srhep_bind_events", "srhep_velocity",
     "srhep_sample", "srhep_sample_dopri5", "srhep_set_debug", "srhep_get_tap", "srhep_launch_count",
+    "srhep_profile",
 )
 
 
@@ -63,6 +65,8 @@ def load() -> C.CDLL:
     lib.srhep_sample_dopri5.argtypes = [vp, vp, vp, i32, f32, f32, i32, vp, C.POINTER(i32), vp]
     lib.srhep_get_tap.restype = C.c_int
     lib.srhep_get_tap.argtypes = [vp, C.c_char_p, vp, C.c_size_t, vp]
+    lib.srhep_profile.restype = C.c_int
+    lib.srhep_profile.argtypes = [vp, vp, f32, vp, C.POINTER(f32), C.POINTER(i32), vp]
     lib.srhep_launch_count.restype = u64
     lib.srhep_launch_count.argtypes = [vp]
     _LIB = lib

@@ -215,10 +215,17 @@ void bf16_free_weights(SrhepHandle* h);
 int bf16_on_bind(SrhepHandle* h);
 int64_t default_pass_tokens(int precision);
 
+struct Profiler {
+    std::vector<cudaEvent_t> ev;       // ev[0] = start; ev[i+1] recorded after launch i
+    std::vector<int> cat;
+};
+
 struct Engine {
     SrhepHandle* h;
     cudaStream_t s;
     int rc = 0;
+    Profiler* prof = nullptr;
+    int cat = 0;
 
     const float* W(size_t off) const { return h->w + off; }
 
@@ -227,6 +234,11 @@ struct Engine {
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) rc = fail(h, SRHEP_E_CUDA, "launch %s: %s", what, cudaGetErrorString(e));
         ++h->launches;
+        if (prof && !rc) {
+            cudaEvent_t evt;
+            if (cudaEventCreate(&evt) != cudaSuccess || cudaEventRecord(evt, s) != cudaSuccess) { rc = fail(h, SRHEP_E_CUDA, "profile event"); return; }
+            prof->ev.push_back(evt); prof->cat.push_back(cat);
+        }
     }
 
     // C = epilogue(A . W^T); A is fp32 here (per-event GEMMs and the whole 'highest' path)
@@ -292,6 +304,7 @@ struct Engine {
         const int* rev = h->row_event + p.r0;
         const int ncol = d.cond + d.noisy_out;
 
+        cat = SRHEP_CAT_EMBED;
         {   // 1. per-event preparation
             EventPrepParams q;
             q.freqs = W(L.freqs); q.half = d.freq_dim / 2;
@@ -324,6 +337,7 @@ struct Engine {
             q.ctx = h->ctx; q.silu_ctx = h->silu_ctx; q.t_emb = d.t_emb; q.cond = d.cond; q.e0 = p.e0;
             if (!rc) { context_kernel<<<nE, 256, 0, s>>>(q); check("context"); }
         }
+        cat = SRHEP_CAT_ADALN;
         {   // 4. every adaLN Linear of the evaluation in one GEMM; 5. context part of feat_0
             GemmEpilogue ep; ep.bias = h->bmod;
             gemm_f32<float>(h->silu_ctx + (size_t)p.e0 * d.ctx, d.ctx, h->wmod, d.ctx, h->mod + (size_t)p.e0 * h->mod_width, h->mod_width,
@@ -338,6 +352,7 @@ struct Engine {
         float* x = h->xres;
         if (!lp) {
             float* a = (float*)h->act_a; float* b = (float*)h->act_b;
+            cat = SRHEP_CAT_FEAT0;
             {   // 6. feat_0 token part + per-event bias, LeakyReLU
                 GemmEpilogue ep; ep.row_bias = h->f0bias; ep.ld_row_bias = H; ep.row_event = rev; ep.act = 1;
                 gemm_f32<float>(h->tok_feat, ncol, W(L.feat0.w), L.feat0.in, x, H, M, H, ncol, ep);
@@ -346,19 +361,27 @@ struct Engine {
             for (int l = 0; l < d.layers; ++l) {
                 const Layout::Layer& y = L.layers[l];
                 const float* ml = mod + (size_t)l * 6 * H;        // shift_msa | scale_msa | gate_msa | shift_mlp | scale_mlp | gate_mlp
+                cat = SRHEP_CAT_LN;
                 ln_mod<float>(x, M, H, W(y.n1w), W(y.n1b), ml, ml + H, rev, 0, a);
+                cat = SRHEP_CAT_QKV;
                 { GemmEpilogue ep; ep.bias = h->bqkv + (size_t)l * 3 * H;
                   gemm_f32<float>(a, H, h->wqkv + (size_t)l * 3 * H * H, H, h->qkv, 3 * H, M, 3 * H, H, ep); }
+                cat = SRHEP_CAT_ATTN;
                 attention_f32(p, h->qkv, b);
+                cat = SRHEP_CAT_OUT;
                 { GemmEpilogue ep; ep.bias = W(y.o.b); ep.gate = ml + 2 * H; ep.ld_gate = h->mod_width; ep.row_event = rev; ep.resid = x; ep.ld_resid = H;
                   gemm_f32<float>(b, H, W(y.o.w), H, x, H, M, H, H, ep); }
+                cat = SRHEP_CAT_LN;
                 ln_mod<float>(x, M, H, W(y.n2w), W(y.n2b), ml + 3 * H, ml + 4 * H, rev, 1, a);
+                cat = SRHEP_CAT_MLP1;
                 { GemmEpilogue ep; ep.bias = W(y.m1.b); ep.act = 1;
                   gemm_f32<float>(a, H, W(y.m1.w), H, b, d.mlp_hid, M, d.mlp_hid, H, ep); }
+                cat = SRHEP_CAT_MLP2;
                 { GemmEpilogue ep; ep.bias = W(y.m2.b); ep.act = 1; ep.gate = ml + 5 * H; ep.ld_gate = h->mod_width; ep.row_event = rev; ep.resid = x; ep.ld_resid = H;
                   gemm_f32<float>(b, d.mlp_hid, W(y.m2.w), d.mlp_hid, x, H, M, H, d.mlp_hid, ep); }
                 if (h->debug && h->tap_layers) tap(h->tap_layers + (size_t)l * h->cap_tap * H, x, M);
             }
+            cat = SRHEP_CAT_HEAD;
             const int hw = d.v_in + d.ctx;
             head_prep<float>(head_params(p, x), a, hw);
             { GemmEpilogue ep; ep.bias = W(L.h1.b); ep.act = 1;
@@ -366,6 +389,7 @@ struct Engine {
         } else {
             bf16_forward(*this, p, rev);
         }
+        cat = SRHEP_CAT_HEAD;
         {   // head tail + ODE update
             HeadTailParams q;
             q.h1 = h->h1buf; q.ldh = d.head_h1; q.M = M;
@@ -522,8 +546,9 @@ int get_graph(SrhepHandle* h, int pi, const StageParams* sp, int* idx) {
 
 // All passes, one evaluation each, direct launches: v = f(t, x) on the whole bound batch.
 int eval_all(SrhepHandle* h, cudaStream_t s, const float* x, float t, const float* t_event, float* v,
-             const float* base, float coef, float* out) {
+             const float* base, float coef, float* out, Profiler* prof = nullptr) {
     Engine E{h, s};
+    E.prof = prof;
     for (const Pass& p : h->passes) {
         StageRef st;
         st.fixed.t = t; st.fixed.coef = coef;
@@ -1011,6 +1036,34 @@ int srhep_sample_dopri5(SrhepHandle* h, const float* x0, const float* tg, int32_
     }
     if (stats_out) { stats_out[0] = nfe; stats_out[1] = n_acc; stats_out[2] = n_rej; }
     return SRHEP_OK;
+}
+
+
+int srhep_profile(SrhepHandle* h, const float* x, float t, float* v, float* ms_by_cat, int32_t* launches_by_cat, void* stream) {
+    if (!h) return SRHEP_E_INVALID;
+    if (!h->bound) return fail(h, SRHEP_E_STATE, "srhep_bind_events must be called first");
+    if (!ms_by_cat || !launches_by_cat || (h->T > 0 && (!x || !v))) return fail(h, SRHEP_E_INVALID, "null argument");
+    for (int i = 0; i < SRHEP_NCAT; ++i) { ms_by_cat[i] = 0.f; launches_by_cat[i] = 0; }
+    if (h->B == 0) return SRHEP_OK;
+    CK(h, cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    Profiler P;
+    cudaEvent_t e0;
+    CK(h, cudaEventCreate(&e0));
+    CK(h, cudaEventRecord(e0, s));
+    P.ev.push_back(e0);
+    int rc = eval_all(h, s, x, t, nullptr, v, nullptr, 0.f, nullptr, &P);
+    cudaError_t ce = cudaStreamSynchronize(s);
+    if (!rc && ce != cudaSuccess) rc = fail(h, SRHEP_E_CUDA, "profile sync: %s", cudaGetErrorString(ce));
+    if (!rc)
+        for (size_t i = 0; i < P.cat.size(); ++i) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, P.ev[i], P.ev[i + 1]) == cudaSuccess && P.cat[i] >= 0 && P.cat[i] < SRHEP_NCAT) {
+                ms_by_cat[P.cat[i]] += ms; ++launches_by_cat[P.cat[i]];
+            }
+        }
+    for (cudaEvent_t e : P.ev) cudaEventDestroy(e);
+    return rc;
 }
 
 int srhep_get_tap(SrhepHandle* h, const char* name, float* out, size_t n_floats, void* stream) {
