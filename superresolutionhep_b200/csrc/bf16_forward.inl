@@ -1,6 +1,192 @@
-// placeholder
-int bf16_pack_weights(SrhepHandle* h, const float*) { return fail(h, SRHEP_E_INVALID, "bf16 path not built yet"); }
-void bf16_free_weights(SrhepHandle*) {}
-int bf16_on_bind(SrhepHandle*) { return 0; }
-void bf16_forward(Engine& E, const Pass&, const int*) { E.rc = fail(E.h, SRHEP_E_INVALID, "bf16 path not built yet"); }
-int64_t default_pass_tokens(int) { return 65536; }
+// Host side of the bf16 tcgen05 path (included by srhep.cu inside its anonymous namespace):
+// weight re-packing into the swizzled shared-memory image, TMA tensor maps over the pass
+// workspace, and the layer schedule of FlowModel.forward with bf16 GEMM operands.
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+    fn = (EncodeTiledFn)p;
+    return fn;
+}
+
+// bf16 row-major [rows, cols] with row pitch ld (elements); box = 64 columns x 128 rows, 128B swizzle
+int make_a_tmap(SrhepHandle* h, CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return fail(h, SRHEP_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kGemmBK, (cuuint32_t)kGemmBM};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(h, SRHEP_E_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu", (int)r,
+                                       (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld);
+    return 0;
+}
+
+uint16_t f2bf(float f) {
+    uint32_t u; memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);     // NaN
+    u += 0x7fffu + ((u >> 16) & 1);                                               // round to nearest even
+    return (uint16_t)(u >> 16);
+}
+
+// W fp32 [N, K] (row pitch ldw) -> image [N / BN][kpad / 64][BN rows x 128 B], 128B-swizzled, K zero-padded
+void pack_weight(std::vector<uint8_t>& img, size_t off, const float* W, int ldw, int N, int K, int kpad, int BN) {
+    const int nkb = kpad / 64;
+    for (int n = 0; n < N; ++n) {
+        const int nt = n / BN, nr = n % BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+            uint8_t* row = img.data() + off + (((size_t)nt * nkb + kb) * BN + nr) * 128;
+            for (int c = 0; c < 8; ++c) {
+                uint16_t* dst = reinterpret_cast<uint16_t*>(row + ((c ^ (nr & 7)) * 16));
+                for (int j = 0; j < 8; ++j) {
+                    const int k = kb * 64 + c * 8 + j;
+                    dst[j] = k < K ? f2bf(W[(size_t)n * ldw + k]) : (uint16_t)0;
+                }
+            }
+        }
+    }
+}
+
+int bf16_pack_weights(SrhepHandle* h, const float* wh) {
+    const SrhepDims& d = h->d; const Layout& L = h->L; Bf16Weights& bw = h->bw;
+    const int H = d.h_dim;
+    if (H != 256 || d.mlp_hid != 256) return fail(h, SRHEP_E_INVALID, "bf16 path: h_dim = mlp_hid = 256 expected (got %d, %d)", H, d.mlp_hid);
+    if (d.head_h1 != 128 || (d.v_in + d.ctx) % 64) return fail(h, SRHEP_E_INVALID, "bf16 path: head_h1 = 128 and (v_in + ctx) %% 64 == 0 expected");
+    if (H / d.heads != 64) return fail(h, SRHEP_E_INVALID, "bf16 path: head dim 64 expected");
+    if (d.layers > 64) return fail(h, SRHEP_E_INVALID, "bf16 path: at most 64 layers");
+    const int ncol = d.cond + d.noisy_out;
+    bw.feat0_kpad = (ncol + 63) / 64 * 64;
+    size_t off = 0;
+    auto take = [&](size_t n_rows, size_t kpad) { size_t o = off; off += n_rows * kpad * 2; return o; };
+    bw.feat0 = take(H, bw.feat0_kpad);
+    for (int l = 0; l < d.layers; ++l) { bw.qkv[l] = take(3 * H, H); bw.out[l] = take(H, H); bw.mlp1[l] = take(H, H); bw.mlp2[l] = take(H, H); }
+    const int hk = d.v_in + d.ctx;
+    bw.head1 = take(d.head_h1, hk);
+    std::vector<uint8_t> img(off);
+    pack_weight(img, bw.feat0, wh + L.feat0.w, L.feat0.in, H, ncol, bw.feat0_kpad, 256);
+    for (int l = 0; l < d.layers; ++l) {
+        const Layout::Layer& y = L.layers[l];
+        const Lin* qkv[3] = {&y.q, &y.k, &y.v};
+        for (int j = 0; j < 3; ++j) pack_weight(img, bw.qkv[l] + (size_t)j * H * H * 2, wh + qkv[j]->w, H, H, H, H, 256);
+        pack_weight(img, bw.out[l], wh + y.o.w, H, H, H, H, 256);
+        pack_weight(img, bw.mlp1[l], wh + y.m1.w, H, H, H, H, 256);
+        pack_weight(img, bw.mlp2[l], wh + y.m2.w, H, H, H, H, 256);
+    }
+    pack_weight(img, bw.head1, wh + L.h1.w, hk, d.head_h1, hk, hk, 128);
+    CK(h, cudaMalloc(&bw.img, img.size()));
+    CK(h, cudaMemcpy(bw.img, img.data(), img.size(), cudaMemcpyHostToDevice));
+    bw.bytes = img.size();
+    bw.bias_layer_stride = 3 * (size_t)H;
+    bw.bias_head1 = bw.bias_layer_stride * d.layers;
+    std::vector<float> b(bw.bias_head1 + d.head_h1);
+    for (int l = 0; l < d.layers; ++l) {
+        const Layout::Layer& y = L.layers[l];
+        memcpy(&b[l * bw.bias_layer_stride], wh + y.o.b, H * sizeof(float));
+        memcpy(&b[l * bw.bias_layer_stride + H], wh + y.m1.b, H * sizeof(float));
+        memcpy(&b[l * bw.bias_layer_stride + 2 * H], wh + y.m2.b, H * sizeof(float));
+    }
+    memcpy(&b[bw.bias_head1], wh + L.h1.b, d.head_h1 * sizeof(float));
+    CK(h, cudaMalloc(&bw.bias, b.size() * sizeof(float)));
+    CK(h, cudaMemcpy(bw.bias, b.data(), b.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CK(h, cudaFuncSetAttribute(gemm_bf16_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_bf16_smem_bytes<256>(4)));
+    CK(h, cudaFuncSetAttribute(gemm_bf16_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_bf16_smem_bytes<128>(hk / 64)));
+    return 0;
+}
+
+void bf16_free_weights(SrhepHandle* h) {
+    if (h->bw.img) cudaFree(h->bw.img);
+    if (h->bw.bias) cudaFree(h->bw.bias);
+    if (h->bw.tok_lp) cudaFree(h->bw.tok_lp);
+    h->bw = Bf16Weights();
+}
+
+// (re)build the A-operand tensor maps after the pass workspace was (re)allocated
+int bf16_on_bind(SrhepHandle* h) {
+    const SrhepDims& d = h->d; Bf16Weights& bw = h->bw;
+    const uint64_t R = h->cap_ws_rows;
+    if (bw.tok_lp) { CK(h, cudaFree(bw.tok_lp)); bw.tok_lp = nullptr; }
+    CK(h, cudaMalloc(&bw.tok_lp, R * bw.feat0_kpad * 2));
+    int rc;
+    if ((rc = make_a_tmap(h, &bw.tm_ln, h->act_a, R, d.h_dim, d.h_dim))) return rc;
+    if ((rc = make_a_tmap(h, &bw.tm_hin, h->act_a, R, d.v_in + d.ctx, d.v_in + d.ctx))) return rc;
+    if ((rc = make_a_tmap(h, &bw.tm_b, h->act_b, R, d.h_dim, d.h_dim))) return rc;
+    if ((rc = make_a_tmap(h, &bw.tm_tok, bw.tok_lp, R, bw.feat0_kpad, bw.feat0_kpad))) return rc;
+    return 0;
+}
+
+int64_t default_pass_tokens(int precision) { return precision == SRHEP_PREC_BF16 ? 32768 : 65536; }
+
+template <int BN>
+void launch_gemm_bf16(Engine& E, const CUtensorMap& tm, int M, int K, int N, const uint8_t* w_img, void* C, int ldc, int out_bf16,
+                      const GemmEpilogue& ep) {
+    if (E.rc || M <= 0) return;
+    GemmBf16Params p;
+    p.M = M; p.num_kb = K / 64; p.w_img = w_img; p.C = C; p.ldc = ldc; p.out_bf16 = out_bf16; p.ep = ep;
+    const int m_tiles = (M + kGemmBM - 1) / kGemmBM, n_tiles = N / BN;
+    dim3 grid(std::max(1, std::min(m_tiles, 148 / n_tiles)), n_tiles);
+    gemm_bf16_kernel<BN><<<grid, kGemmThreads, gemm_bf16_smem_bytes<BN>(p.num_kb), E.s>>>(tm, p);
+    E.check("gemm_bf16");
+}
+
+void bf16_forward(Engine& E, const Pass& p, const int* rev) {
+    SrhepHandle* h = E.h;
+    const SrhepDims& d = h->d; const Layout& L = h->L; Bf16Weights& bw = h->bw;
+    const int M = p.r1 - p.r0, H = d.h_dim, ncol = d.cond + d.noisy_out;
+    float* x = h->xres;
+    const float* mod = h->mod;
+    __nv_bfloat16* a = (__nv_bfloat16*)h->act_a; __nv_bfloat16* b = (__nv_bfloat16*)h->act_b;
+    __nv_bfloat16* qkv = (__nv_bfloat16*)h->qkv_lp;
+    E.cat = SRHEP_CAT_FEAT0;
+    if (!E.rc) {
+        const int grid = (int)std::min<size_t>(((size_t)M * bw.feat0_kpad + 255) / 256, 148 * 16);
+        cast_pad_bf16_kernel<<<grid, 256, 0, E.s>>>(h->tok_feat, ncol, bw.tok_lp, bw.feat0_kpad, M, ncol);
+        E.check("cast_pad_bf16");
+    }
+    { GemmEpilogue ep; ep.row_bias = h->f0bias; ep.ld_row_bias = H; ep.row_event = rev; ep.act = 1;
+      launch_gemm_bf16<256>(E, bw.tm_tok, M, bw.feat0_kpad, H, bw.img + bw.feat0, x, H, 0, ep); }
+    E.tap(h->tap_feat0, x, M);
+    for (int l = 0; l < d.layers; ++l) {
+        const Layout::Layer& y = L.layers[l];
+        const float* ml = mod + (size_t)l * 6 * H;
+        const float* bl = bw.bias + l * bw.bias_layer_stride;
+        E.cat = SRHEP_CAT_LN;
+        E.ln_mod<__nv_bfloat16>(x, M, H, E.W(y.n1w), E.W(y.n1b), ml, ml + H, rev, 0, a);
+        E.cat = SRHEP_CAT_QKV;
+        { GemmEpilogue ep; ep.bias = h->bqkv + (size_t)l * 3 * H;
+          launch_gemm_bf16<256>(E, bw.tm_ln, M, H, 3 * H, bw.img + bw.qkv[l], qkv, 3 * H, 1, ep); }
+        E.cat = SRHEP_CAT_ATTN;
+        E.attention_simt<__nv_bfloat16>(p, qkv, b);
+        E.cat = SRHEP_CAT_OUT;
+        { GemmEpilogue ep; ep.bias = bl; ep.gate = ml + 2 * H; ep.ld_gate = h->mod_width; ep.row_event = rev; ep.resid = x; ep.ld_resid = H;
+          launch_gemm_bf16<256>(E, bw.tm_b, M, H, H, bw.img + bw.out[l], x, H, 0, ep); }
+        E.cat = SRHEP_CAT_LN;
+        E.ln_mod<__nv_bfloat16>(x, M, H, E.W(y.n2w), E.W(y.n2b), ml + 3 * H, ml + 4 * H, rev, 1, a);
+        E.cat = SRHEP_CAT_MLP1;
+        { GemmEpilogue ep; ep.bias = bl + H; ep.act = 1;
+          launch_gemm_bf16<256>(E, bw.tm_ln, M, H, H, bw.img + bw.mlp1[l], b, H, 1, ep); }
+        E.cat = SRHEP_CAT_MLP2;
+        { GemmEpilogue ep; ep.bias = bl + 2 * H; ep.act = 1; ep.gate = ml + 5 * H; ep.ld_gate = h->mod_width; ep.row_event = rev; ep.resid = x; ep.ld_resid = H;
+          launch_gemm_bf16<256>(E, bw.tm_b, M, H, H, bw.img + bw.mlp2[l], x, H, 0, ep); }
+        if (h->debug && h->tap_layers) E.tap(h->tap_layers + (size_t)l * h->cap_tap * H, x, M);
+    }
+    E.cat = SRHEP_CAT_HEAD;
+    const int hw = d.v_in + d.ctx;
+    if (getenv("SRHEP_HEAD_FP32")) {
+        E.head_prep<float>(E.head_params(p, x), (float*)h->act_a, hw);
+        GemmEpilogue ep; ep.bias = E.W(L.h1.b); ep.act = 1;
+        E.gemm_f32<float>((float*)h->act_a, hw, E.W(L.h1.w), hw, h->h1buf, d.head_h1, M, d.head_h1, hw, ep);
+    } else {
+    E.head_prep<__nv_bfloat16>(E.head_params(p, x), a, hw);
+    { GemmEpilogue ep; ep.bias = bw.bias + bw.bias_head1; ep.act = 1;
+      launch_gemm_bf16<128>(E, bw.tm_hin, M, hw, d.head_h1, bw.img + bw.head1, h->h1buf, d.head_h1, 0, ep); }
+    }
+}

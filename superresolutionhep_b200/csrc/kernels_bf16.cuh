@@ -1,4 +1,317 @@
-// placeholder, replaced by the tcgen05 kernels
+// bf16 tensor-core kernels for sm_100a: tcgen05.mma with TMEM accumulators, operands staged
+// in shared memory by TMA (cp.async.bulk.tensor for activations, cp.async.bulk for the
+// pre-swizzled weight image), mbarrier pipelines, warp-specialised roles.
+//
+// Shared-memory operand layout (both A and B, "K-major, 128-byte swizzle"): a k-block is
+// 64 bf16 = 128 bytes per row; rows are contiguous (128 B apart); 8 rows = one 1024-byte
+// swizzle atom; inside an atom the 16-byte chunk c of row r sits at chunk position
+// c ^ (r & 7).  This is what CU_TENSOR_MAP_SWIZZLE_128B produces and what the UMMA shared
+// memory descriptor with layout_type = SWIZZLE_128B, SBO = 1024 expects.
 #pragma once
+#include <cuda.h>
+
 #include "common.cuh"
-namespace srhep { struct Bf16Weights {}; }
+
+namespace srhep {
+
+// ------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}"
+        ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, bf16 in, fp32 accumulate; issued by ONE thread
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread t = lane base + t)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor: K-major operand, 128-byte swizzle, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// UMMA instruction descriptor: A, B bf16 (K-major both), D fp32, M x N tile
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// ------------------------------------------------------------------------------------
+// GEMM  C[M, N] = epilogue(A[M, K] . W[N, K]^T)      A, W bf16; fp32 accumulation in TMEM
+//
+// Persistent CTAs: blockIdx.y picks a BN-wide slice of W whose pre-swizzled image (all of
+// K) is loaded ONCE into shared memory; the CTA then walks M tiles of 128 rows, streaming A
+// k-blocks through a 4-stage TMA ring.  Two TMEM accumulators (2 x BN columns) let the MMA of
+// tile i+1 run under the epilogue of tile i.
+//   warp 0: TMA producer   warp 1: TMEM allocator + MMA issuer   warps 2-5: epilogue
+// ------------------------------------------------------------------------------------
+constexpr int kGemmBM = 128;
+constexpr int kGemmBK = 64;
+constexpr int kGemmStages = 4;
+constexpr int kGemmThreads = 192;
+
+struct GemmBf16Params {
+    int M;                  // valid rows
+    int num_kb;             // K / 64 (K is zero-padded to a multiple of 64 in A and W)
+    const uint8_t* w_img;   // [N / BN][num_kb][BN x 128 B] pre-swizzled bf16 weights
+    void* C; int ldc; int out_bf16;
+    GemmEpilogue ep;
+};
+
+template <int BN>
+constexpr size_t gemm_bf16_smem_bytes(int num_kb) {
+    return 1024 /*alignment slack*/ + (size_t)num_kb * BN * 128 + (size_t)kGemmStages * kGemmBM * 128 + 256;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, GemmBf16Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* s_w = smem;                                            // num_kb x (BN x 128 B)
+    uint8_t* s_a = s_w + (size_t)p.num_kb * BN * 128;               // kGemmStages x (128 x 128 B)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_a + (size_t)kGemmStages * kGemmBM * 128);
+    uint64_t* full = bars;                       // [stages]  TMA -> MMA
+    uint64_t* empty = bars + kGemmStages;        // [stages]  MMA -> TMA
+    uint64_t* w_full = bars + 2 * kGemmStages;   // weights landed
+    uint64_t* t_full = w_full + 1;               // [2] accumulator ready   MMA -> epilogue
+    uint64_t* t_empty = t_full + 2;              // [2] accumulator drained epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tiles = (p.M + kGemmBM - 1) / kGemmBM;
+    const int n_tile = blockIdx.y;
+    constexpr uint32_t kTmemCols = 2 * BN;       // 256 or 512: a power of two >= 32
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_a);
+        for (int i = 0; i < kGemmStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(w_full, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
+        mbar_fence_init();
+    }
+    if (warp == 1) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // weights: one bulk copy per k-block
+            const uint32_t wbytes = (uint32_t)BN * 128;
+            mbar_expect_tx(w_full, wbytes * p.num_kb);
+            const uint8_t* src = p.w_img + (size_t)n_tile * p.num_kb * wbytes;
+            for (int kb = 0; kb < p.num_kb; ++kb) bulk_load(s_w + (size_t)kb * wbytes, src + (size_t)kb * wbytes, wbytes, w_full);
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < m_tiles; t += gridDim.x) {
+                for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+                    const uint32_t s = it % kGemmStages, ph = (it / kGemmStages) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    mbar_expect_tx(&full[s], kGemmBM * 128);
+                    tma_load_2d(s_a + (size_t)s * kGemmBM * 128, &tmap_a, &full[s], kb * kGemmBK, t * kGemmBM);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = umma_idesc_bf16(kGemmBM, BN);
+        mbar_wait(w_full, 0);
+        uint32_t it = 0, tile_i = 0;
+        for (int t = blockIdx.x; t < m_tiles; t += gridDim.x, ++tile_i) {
+            const uint32_t a = tile_i & 1, aph = (tile_i >> 1) & 1;
+            mbar_wait(&t_empty[a], aph ^ 1);
+            tc_fence_after();
+            for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+                const uint32_t s = it % kGemmStages, ph = (it / kGemmStages) & 1;
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t a_addr = smem_u32(s_a + (size_t)s * kGemmBM * 128);
+                    const uint32_t b_addr = smem_u32(s_w + (size_t)kb * BN * 128);
+#pragma unroll
+                    for (int k = 0; k < kGemmBK / 16; ++k)
+                        umma_bf16(tmem_base + a * BN, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                                  (uint32_t)((kb | k) != 0));
+                    tc_commit(&empty[s]);                           // frees the A stage when these MMAs retire
+                    if (kb == p.num_kb - 1) tc_commit(&t_full[a]);  // accumulator complete
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        const int q = warp & 3;                                     // TMEM lane quarter this warp may read
+        const GemmEpilogue& ep = p.ep;
+        uint32_t tile_i = 0;
+        for (int t = blockIdx.x; t < m_tiles; t += gridDim.x, ++tile_i) {
+            const uint32_t a = tile_i & 1, aph = (tile_i >> 1) & 1;
+            mbar_wait(&t_full[a], aph);
+            tc_fence_after();
+            const int row = t * kGemmBM + q * 32 + lane;
+            const bool valid = row < p.M;
+            const int evt = valid ? (ep.row_event ? ep.row_event[row] : row) : 0;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * BN + c0, r);
+                tmem_ld_wait();
+                if (valid) {
+                    const int col0 = n_tile * BN + c0;
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                    if (ep.bias) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + j));
+                            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                        }
+                    }
+                    if (ep.row_bias) {
+                        const float* rb = ep.row_bias + (size_t)evt * ep.ld_row_bias + col0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(rb + j);
+                            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                        }
+                    }
+                    if (ep.act == 1) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = leaky_relu(v[j]);
+                    }
+                    if (ep.resid) {
+                        const float* g = ep.gate + (size_t)evt * ep.ld_gate + col0;
+                        const float* rs = ep.resid + (size_t)row * ep.ld_resid + col0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 g4 = *reinterpret_cast<const float4*>(g + j);
+                            const float4 r4 = *reinterpret_cast<const float4*>(rs + j);
+                            v[j] = fmaf(g4.x, v[j], r4.x); v[j + 1] = fmaf(g4.y, v[j + 1], r4.y);
+                            v[j + 2] = fmaf(g4.z, v[j + 2], r4.z); v[j + 3] = fmaf(g4.w, v[j + 3], r4.w);
+                        }
+                    }
+                    if (p.out_bf16) {
+                        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col0);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            dst[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                                pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+                    } else {
+                        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&t_empty[a]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
+}
+
+// fp32 [rows, cols] (ld) -> bf16 [rows, cols_pad] zero-padded (GEMM A operands that are not
+// produced in bf16 by their own kernel)
+__global__ void cast_pad_bf16_kernel(const float* __restrict__ src, int ld_src, __nv_bfloat16* dst, int ld_dst, int rows, int cols) {
+    const size_t n = (size_t)rows * ld_dst;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / ld_dst), c = (int)(i % ld_dst);
+        dst[i] = __float2bfloat16_rn(c < cols ? src[(size_t)r * ld_src + c] : 0.f);
+    }
+}
+
+struct Bf16Weights {
+    uint8_t* img = nullptr;          // all pre-swizzled weight images, one allocation
+    size_t bytes = 0;
+    // offsets (bytes) into img
+    size_t feat0 = 0, head1 = 0;
+    size_t qkv[64] = {0}, out[64] = {0}, mlp1[64] = {0}, mlp2[64] = {0};
+    float* bias = nullptr;           // 16-byte aligned copies: per layer [out | mlp1 | mlp2], then head1
+    size_t bias_layer_stride = 0, bias_head1 = 0;
+    __nv_bfloat16* tok_lp = nullptr; // [rows, feat0 K padded] bf16 copy of tok_feat (feat_0 GEMM A operand)
+    int feat0_kpad = 0;
+    CUtensorMap tm_ln, tm_hin, tm_b, tm_tok;      // A-operand maps over the pass workspace
+};
+
+}  // namespace srhep

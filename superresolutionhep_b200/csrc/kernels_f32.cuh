@@ -424,10 +424,24 @@ __global__ void __launch_bounds__(256) ln_mod_kernel(LnModParams p, OutT* out, i
 // ------------------------------------------------------------------------------------
 struct AttnWork { int q_row, q_len, k_row, k_len; };
 
-template <int HD>
-__global__ void __launch_bounds__(128) attn_f32_kernel(const float* __restrict__ Q, int ldq,
-                                                       const float* __restrict__ Kp, const float* __restrict__ Vp, int ldkv,
-                                                       float* O, int ldo, const AttnWork* work, float inv_scale) {
+__device__ __forceinline__ float4 load4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 load4(const __nv_bfloat16* p) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x), b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+    const float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+    return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+__device__ __forceinline__ void store4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void store4(__nv_bfloat16* p, float4 v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u; u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = u;
+}
+
+template <int HD, typename T>
+__global__ void __launch_bounds__(128) attn_f32_kernel(const T* __restrict__ Q, int ldq,
+                                                       const T* __restrict__ Kp, const T* __restrict__ Vp, int ldkv,
+                                                       T* O, int ldo, const AttnWork* work, float inv_scale) {
     constexpr int KT = 32;
     __shared__ __align__(16) float Ks[KT][HD];
     __shared__ __align__(16) float Vs[KT][HD];
@@ -437,10 +451,10 @@ __global__ void __launch_bounds__(128) attn_f32_kernel(const float* __restrict__
     const bool active = tid < w.q_len;
     float q[HD], acc[HD];
     if (active) {
-        const float* qp = Q + (size_t)(w.q_row + tid) * ldq + head * HD;
+        const T* qp = Q + (size_t)(w.q_row + tid) * ldq + head * HD;
 #pragma unroll
         for (int d = 0; d < HD; d += 4) {
-            const float4 t4 = *reinterpret_cast<const float4*>(qp + d);
+            const float4 t4 = load4(qp + d);
             q[d] = t4.x * inv_scale; q[d + 1] = t4.y * inv_scale; q[d + 2] = t4.z * inv_scale; q[d + 3] = t4.w * inv_scale;
         }
     }
@@ -453,8 +467,8 @@ __global__ void __launch_bounds__(128) attn_f32_kernel(const float* __restrict__
         for (int i = tid; i < kt * (HD / 4); i += blockDim.x) {
             const int kk = i / (HD / 4), d4 = i % (HD / 4);
             const size_t off = (size_t)(w.k_row + k0 + kk) * ldkv + head * HD + d4 * 4;
-            *reinterpret_cast<float4*>(&Ks[kk][d4 * 4]) = *reinterpret_cast<const float4*>(Kp + off);
-            *reinterpret_cast<float4*>(&Vs[kk][d4 * 4]) = *reinterpret_cast<const float4*>(Vp + off);
+            *reinterpret_cast<float4*>(&Ks[kk][d4 * 4]) = load4(Kp + off);
+            *reinterpret_cast<float4*>(&Vs[kk][d4 * 4]) = load4(Vp + off);
         }
         __syncthreads();
         if (!active) continue;
@@ -498,10 +512,10 @@ __global__ void __launch_bounds__(128) attn_f32_kernel(const float* __restrict__
     }
     if (active) {
         const float inv = l > 0.f ? 1.f / l : 0.f;    // no keys: zero row, like masked_fill(0)
-        float* op = O + (size_t)(w.q_row + tid) * ldo + head * HD;
+        T* op = O + (size_t)(w.q_row + tid) * ldo + head * HD;
 #pragma unroll
         for (int d = 0; d < HD; d += 4)
-            *reinterpret_cast<float4*>(op + d) = make_float4(acc[d] * inv, acc[d + 1] * inv, acc[d + 2] * inv, acc[d + 3] * inv);
+            store4(op + d, make_float4(acc[d] * inv, acc[d + 1] * inv, acc[d + 2] * inv, acc[d + 3] * inv));
     }
 }
 

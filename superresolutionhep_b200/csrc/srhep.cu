@@ -257,7 +257,9 @@ struct Engine {
         return n;
     }
 
-    void attention_f32(const Pass& p, const float* qkv, float* out) {
+    // reference-order softmax(QK^T / sqrt(hd)) V on CUDA cores (fp32 math; T = storage type)
+    template <typename T>
+    void attention_simt(const Pass& p, const T* qkv, T* out) {
         if (rc || p.w1 == p.w0) return;
         const SrhepDims& d = h->d;
         const int hd = d.h_dim / d.heads;
@@ -265,10 +267,10 @@ struct Engine {
         const float inv = 1.0f / sqrtf((float)hd);
         const AttnWork* wk = h->attn_work + p.w0;
         const int ld = 3 * d.h_dim;
-        if (hd == 64) attn_f32_kernel<64><<<grid, 128, 0, s>>>(qkv, ld, qkv + d.h_dim, qkv + 2 * d.h_dim, ld, out, d.h_dim, wk, inv);
-        else if (hd == 32) attn_f32_kernel<32><<<grid, 128, 0, s>>>(qkv, ld, qkv + d.h_dim, qkv + 2 * d.h_dim, ld, out, d.h_dim, wk, inv);
-        else attn_f32_kernel<16><<<grid, 128, 0, s>>>(qkv, ld, qkv + d.h_dim, qkv + 2 * d.h_dim, ld, out, d.h_dim, wk, inv);
-        check("attn_f32");
+        if (hd == 64) attn_f32_kernel<64, T><<<grid, 128, 0, s>>>(qkv, ld, qkv + d.h_dim, qkv + 2 * d.h_dim, ld, out, d.h_dim, wk, inv);
+        else if (hd == 32) attn_f32_kernel<32, T><<<grid, 128, 0, s>>>(qkv, ld, qkv + d.h_dim, qkv + 2 * d.h_dim, ld, out, d.h_dim, wk, inv);
+        else attn_f32_kernel<16, T><<<grid, 128, 0, s>>>(qkv, ld, qkv + d.h_dim, qkv + 2 * d.h_dim, ld, out, d.h_dim, wk, inv);
+        check("attn_simt");
     }
 
     template <typename OutT>
@@ -367,7 +369,7 @@ struct Engine {
                 { GemmEpilogue ep; ep.bias = h->bqkv + (size_t)l * 3 * H;
                   gemm_f32<float>(a, H, h->wqkv + (size_t)l * 3 * H * H, H, h->qkv, 3 * H, M, 3 * H, H, ep); }
                 cat = SRHEP_CAT_ATTN;
-                attention_f32(p, h->qkv, b);
+                attention_simt<float>(p, h->qkv, b);
                 cat = SRHEP_CAT_OUT;
                 { GemmEpilogue ep; ep.bias = W(y.o.b); ep.gate = ml + 2 * H; ep.ld_gate = h->mod_width; ep.row_event = rev; ep.resid = x; ep.ld_resid = H;
                   gemm_f32<float>(b, H, W(y.o.w), H, x, H, M, H, H, ep); }
@@ -473,7 +475,7 @@ int alloc_workspace(SrhepHandle* h) {
     if ((rc = re(h->tok_feat, R * (d.cond + d.noisy_out) * sizeof(float)))) return rc;
     if ((rc = re(h->xres, R * d.h_dim * sizeof(float)))) return rc;
     if ((rc = re(h->h1buf, R * d.head_h1 * sizeof(float)))) return rc;
-    if ((rc = re(h->act_a, R * wide * es))) return rc;
+    if ((rc = re(h->act_a, R * wide * 4))) return rc;
     if ((rc = re(h->act_b, R * std::max(d.h_dim, d.mlp_hid) * es))) return rc;
     if (h->precision == SRHEP_PREC_BF16) { if ((rc = re(h->qkv_lp, R * 3 * d.h_dim * 2))) return rc; }
     else { if ((rc = re(h->qkv, R * 3 * d.h_dim * sizeof(float)))) return rc; }
