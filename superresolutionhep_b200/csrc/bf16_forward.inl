@@ -98,6 +98,7 @@ int bf16_pack_weights(SrhepHandle* h, const float* wh) {
     CK(h, cudaMalloc(&bw.bias, b.size() * sizeof(float)));
     CK(h, cudaMemcpy(bw.bias, b.data(), b.size() * sizeof(float), cudaMemcpyHostToDevice));
     CK(h, cudaFuncSetAttribute(gemm_bf16_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_bf16_smem_bytes<256>(4)));
+    CK(h, cudaFuncSetAttribute(attn_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmemBytes));
     CK(h, cudaFuncSetAttribute(gemm_bf16_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_bf16_smem_bytes<128>(hk / 64)));
     return 0;
 }
@@ -120,6 +121,7 @@ int bf16_on_bind(SrhepHandle* h) {
     if ((rc = make_a_tmap(h, &bw.tm_hin, h->act_a, R, d.v_in + d.ctx, d.v_in + d.ctx))) return rc;
     if ((rc = make_a_tmap(h, &bw.tm_b, h->act_b, R, d.h_dim, d.h_dim))) return rc;
     if ((rc = make_a_tmap(h, &bw.tm_tok, bw.tok_lp, R, bw.feat0_kpad, bw.feat0_kpad))) return rc;
+    if ((rc = make_a_tmap(h, &bw.tm_qkv, h->qkv_lp, R, 3 * d.h_dim, 3 * d.h_dim))) return rc;
     return 0;
 }
 
@@ -135,6 +137,20 @@ void launch_gemm_bf16(Engine& E, const CUtensorMap& tm, int M, int K, int N, con
     dim3 grid(std::max(1, std::min(m_tiles, 148 / n_tiles)), n_tiles);
     gemm_bf16_kernel<BN><<<grid, kGemmThreads, gemm_bf16_smem_bytes<BN>(p.num_kb), E.s>>>(tm, p);
     E.check("gemm_bf16");
+}
+
+void launch_attn_bf16(Engine& E, const Pass& p, __nv_bfloat16* out) {
+    if (E.rc || p.w1 == p.w0) return;
+    SrhepHandle* h = E.h;
+    const SrhepDims& d = h->d;
+    AttnBf16Params q;
+    static_assert(sizeof(AttnItem) == sizeof(AttnWork), "work item layout");
+    q.items = reinterpret_cast<const AttnItem*>(h->attn_work + p.w0); q.n_items = p.w1 - p.w0;
+    q.out = out; q.ldo = d.h_dim; q.h_dim = d.h_dim;
+    q.scale_log2 = 1.4426950408889634f / sqrtf((float)(d.h_dim / d.heads));
+    dim3 grid(std::max(1, std::min(q.n_items, 2 * 148 / d.heads)), d.heads);
+    attn_bf16_kernel<<<grid, kAttnThreads, kAttnSmemBytes, E.s>>>(h->bw.tm_qkv, q);
+    E.check("attn_bf16");
 }
 
 void bf16_forward(Engine& E, const Pass& p, const int* rev) {
@@ -164,7 +180,8 @@ void bf16_forward(Engine& E, const Pass& p, const int* rev) {
         { GemmEpilogue ep; ep.bias = h->bqkv + (size_t)l * 3 * H;
           launch_gemm_bf16<256>(E, bw.tm_ln, M, H, 3 * H, bw.img + bw.qkv[l], qkv, 3 * H, 1, ep); }
         E.cat = SRHEP_CAT_ATTN;
-        E.attention_simt<__nv_bfloat16>(p, qkv, b);
+        if (getenv("SRHEP_ATTN_SIMT")) E.attention_simt<__nv_bfloat16>(p, qkv, b);
+        else launch_attn_bf16(E, p, b);
         E.cat = SRHEP_CAT_OUT;
         { GemmEpilogue ep; ep.bias = bl; ep.gate = ml + 2 * H; ep.ld_gate = h->mod_width; ep.row_event = rev; ep.resid = x; ep.ld_resid = H;
           launch_gemm_bf16<256>(E, bw.tm_b, M, H, H, bw.img + bw.out[l], x, H, 0, ep); }

@@ -291,6 +291,255 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
 }
 
+
+// 32 registers per thread -> 32 lanes x 32 consecutive fp32 columns of TMEM
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+          "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+          "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+          "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float fast_exp2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// UMMA descriptor for an MN-major operand stored as [k rows][64 elements = 128 B], 128-byte
+// swizzle (8 k-rows per 1024-byte atom): V as the B operand of P.V, straight from its
+// row-major [key][head_dim] TMA tile.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(8192 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_bmn(int M, int N) { return umma_idesc_bf16(M, N) | (1u << 16); }
+
+// ------------------------------------------------------------------------------------
+// Varlen attention on tensor cores (head_dim 64).  One work item = (event, 128-query tile);
+// blockIdx.y = head.  Keys/values of the item's event are streamed in tiles of 128:
+//     S = Q K^T  (tcgen05, TMEM cols [0,128))  ->  online softmax in registers (one thread
+//     per query row, fp32, exp2 with the 1/sqrt(hd) scale folded in)  ->  P (bf16) to shared
+//     memory in the UMMA layout  ->  O += P V  (tcgen05, TMEM cols [128,192)).
+// Padded cells never enter (models/attention.py:238-265 + models/utils.py:23-34 restricted
+// to real rows; keys past the event's end inside the last tile are masked to -inf).
+// The running max is only raised when it grows by more than 8 (log2 units), so the O
+// accumulator in TMEM is rescaled rarely; the final 1/l normalisation makes that exact.
+//   warp 0: TMA producer   warp 1: TMEM allocator + MMA issuer   warps 2-5: softmax + epilogue
+// ------------------------------------------------------------------------------------
+constexpr int kAttnThreads = 192;
+constexpr int kAttnKvStages = 2;
+constexpr int kAttnTile = 128;
+constexpr size_t kAttnSmemBytes = 16384 /*Q*/ + kAttnKvStages * 32768 /*K,V*/ + 32768 /*P*/ + 256;   // x2 CTAs fits one SM
+
+struct AttnItem { int q_row, q_len, k_row, k_len; };     // same layout as AttnWork (rows pass-local)
+
+struct AttnBf16Params {
+    const AttnItem* items; int n_items;
+    __nv_bfloat16* out; int ldo;      // [rows, h_dim]
+    int h_dim;                        // column offsets: q = head*64, k = h_dim + head*64, v = 2*h_dim + head*64
+    float scale_log2;                 // log2(e) / sqrt(head_dim)
+};
+
+__global__ void __launch_bounds__(kAttnThreads, 2) attn_bf16_kernel(const __grid_constant__ CUtensorMap tmap_qkv, AttnBf16Params p) {
+    extern __shared__ __align__(1024) uint8_t attn_smem[];      // no static smem in this kernel: the dynamic window starts 1024-aligned
+    uint8_t* smem = attn_smem;
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    uint8_t* s_q = smem;
+    uint8_t* s_kv = s_q + 16384;                       // stage s: K at +0, V at +16384
+    uint8_t* s_p = s_kv + kAttnKvStages * 32768;       // 2 k-blocks of [128 x 128 B]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_p + 32768);
+    uint64_t* q_full = bars;            // TMA -> MMA
+    uint64_t* q_empty = bars + 1;       // MMA -> TMA   (all QK^T of the item retired)
+    uint64_t* kv_full = bars + 2;       // [stages]
+    uint64_t* kv_empty = bars + 4;      // [stages]     (PV of the tile retired)
+    uint64_t* s_full = bars + 6;        // MMA -> softmax
+    uint64_t* s_empty = bars + 7;       // softmax -> MMA (S read out of TMEM)
+    uint64_t* p_full = bars + 8;        // softmax -> MMA (P in smem, O rescaled)
+    uint64_t* pv_done = bars + 9;       // MMA -> softmax (PV retired: P buffer free, O readable)
+    uint64_t* o_empty = bars + 10;      // epilogue -> MMA (O read out)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int head = blockIdx.y;
+    constexpr uint32_t kTmemCols = 256;
+    constexpr uint32_t kColS = 0, kColO = 128;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_qkv);
+        mbar_init(q_full, 1); mbar_init(q_empty, 1);
+        for (int i = 0; i < kAttnKvStages; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+        mbar_init(s_full, 1); mbar_init(s_empty, 4); mbar_init(p_full, 4); mbar_init(pv_done, 1); mbar_init(o_empty, 4);
+        mbar_fence_init();
+    }
+    if (warp == 1) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0, item_i = 0;
+            for (int w = blockIdx.x; w < p.n_items; w += gridDim.x, ++item_i) {
+                const AttnItem a = p.items[w];
+                mbar_wait(q_empty, (item_i & 1) ^ 1);
+                mbar_expect_tx(q_full, 16384);
+                tma_load_2d(s_q, &tmap_qkv, q_full, head * 64, a.q_row);
+                const int n_kv = (a.k_len + kAttnTile - 1) / kAttnTile;
+                for (int j = 0; j < n_kv; ++j, ++it) {
+                    const uint32_t s = it % kAttnKvStages, ph = (it / kAttnKvStages) & 1;
+                    mbar_wait(&kv_empty[s], ph ^ 1);
+                    mbar_expect_tx(&kv_full[s], 32768);
+                    tma_load_2d(s_kv + s * 32768, &tmap_qkv, &kv_full[s], p.h_dim + head * 64, a.k_row + j * kAttnTile);
+                    tma_load_2d(s_kv + s * 32768 + 16384, &tmap_qkv, &kv_full[s], 2 * p.h_dim + head * 64, a.k_row + j * kAttnTile);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);          // S = Q K^T
+        constexpr uint32_t idesc_o = umma_idesc_bf16_bmn(128, 64);       // O = P V (V MN-major)
+        uint32_t it = 0, item_i = 0;
+        for (int w = blockIdx.x; w < p.n_items; w += gridDim.x, ++item_i) {
+            const AttnItem a = p.items[w];
+            const int n_kv = (a.k_len + kAttnTile - 1) / kAttnTile;
+            mbar_wait(q_full, item_i & 1);
+            for (int j = 0; j < n_kv; ++j, ++it) {
+                const uint32_t s = it % kAttnKvStages, ph = (it / kAttnKvStages) & 1;
+                mbar_wait(&kv_full[s], ph);
+                mbar_wait(s_empty, (it & 1) ^ 1);                        // softmax has read the previous S
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t qa = smem_u32(s_q), ka = smem_u32(s_kv + s * 32768);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(tmem_base + kColS, umma_desc_sw128(qa + k * 32), umma_desc_sw128(ka + k * 32), idesc_s, (uint32_t)(k != 0));
+                    tc_commit(s_full);
+                    if (j == n_kv - 1) tc_commit(q_empty);
+                }
+                __syncwarp();
+                mbar_wait(p_full, it & 1);                               // P written, O rescaled
+                if (j == 0) mbar_wait(o_empty, (item_i & 1) ^ 1);        // previous item's O has been read out
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t pa = smem_u32(s_p), va = smem_u32(s_kv + s * 32768 + 16384);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        umma_bf16(tmem_base + kColO, umma_desc_sw128(pa + (k >> 2) * 16384 + (k & 3) * 32), umma_desc_mn_sw128(va + k * 2048),
+                                  idesc_o, (uint32_t)((j | k) != 0));
+                    tc_commit(&kv_empty[s]);
+                    tc_commit(pv_done);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;                                   // query row inside the tile = TMEM lane
+        const uint32_t t_lane = (uint32_t)(q * 32) << 16;
+        uint32_t it = 0, item_i = 0;
+        for (int w = blockIdx.x; w < p.n_items; w += gridDim.x, ++item_i) {
+            const AttnItem a = p.items[w];
+            const int n_kv = (a.k_len + kAttnTile - 1) / kAttnTile;
+            float m_ref = -INFINITY, l = 0.f;
+            for (int j = 0; j < n_kv; ++j, ++it) {
+                const int kv_valid = min(kAttnTile, a.k_len - j * kAttnTile);
+                mbar_wait(s_full, it & 1);
+                tc_fence_after();
+                // pass 1: row maximum (scaled to log2 units)
+                float mx = -INFINITY;
+#pragma unroll 1
+                for (int c0 = 0; c0 < kAttnTile; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + t_lane + kColS + c0, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) if (c0 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+                }
+                mx *= p.scale_log2;
+                float corr = 1.f;
+                bool rescale = false;
+                if (mx > m_ref + 8.f) {                                  // first tile: m_ref = -inf
+                    if (j > 0) { corr = fast_exp2(m_ref - mx); rescale = true; }
+                    m_ref = mx;
+                }
+                l *= corr;
+                // the P buffer and the O accumulator are free once PV of the previous tile retired
+                if (it > 0) mbar_wait(pv_done, (it - 1) & 1);
+                tc_fence_after();
+                // pass 2: P = exp2(s * c - m_ref) -> bf16 -> shared memory (UMMA K-major, 128B swizzle)
+#pragma unroll 1
+                for (int c0 = 0; c0 < kAttnTile; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + t_lane + kColS + c0, r);
+                    tmem_ld_wait();
+                    float pv[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float e = fast_exp2(fmaf(__uint_as_float(r[i]), p.scale_log2, -m_ref));
+                        pv[i] = (c0 + i < kv_valid) ? e : 0.f;
+                        l += pv[i];
+                    }
+                    uint8_t* prow = s_p + (c0 >> 6) * 16384 + row * 128;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const int chunk = ((c0 & 63) >> 3) + g;
+                        *reinterpret_cast<uint4*>(prow + ((chunk ^ (row & 7)) << 4)) =
+                            make_uint4(pack_bf16x2(pv[8 * g], pv[8 * g + 1]), pack_bf16x2(pv[8 * g + 2], pv[8 * g + 3]),
+                                       pack_bf16x2(pv[8 * g + 4], pv[8 * g + 5]), pack_bf16x2(pv[8 * g + 6], pv[8 * g + 7]));
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(s_empty);                     // S may be overwritten by the next QK^T
+                if (__any_sync(0xffffffffu, rescale)) {                  // rare: raise the reference maximum
+#pragma unroll 1
+                    for (int c0 = 0; c0 < 64; c0 += 32) {
+                        uint32_t r[32];
+                        tmem_ld32(tmem_base + t_lane + kColO + c0, r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * corr);
+                        tmem_st32(tmem_base + t_lane + kColO + c0, r);
+                    }
+                    tmem_st_wait();
+                }
+                fence_async_smem();                                       // P stores -> visible to the tensor core proxy
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(p_full);
+            }
+            // epilogue: O / l -> bf16 -> global
+            mbar_wait(pv_done, (it - 1) & 1);
+            tc_fence_after();
+            const float inv = l > 0.f ? 1.f / l : 0.f;
+            const bool valid = row < a.q_len;
+            __nv_bfloat16* orow = p.out + (size_t)(a.q_row + row) * p.ldo + head * 64;
+#pragma unroll 1
+            for (int c0 = 0; c0 < 64; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + t_lane + kColO + c0, r);
+                tmem_ld_wait();
+                if (valid) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g)
+                        *reinterpret_cast<uint4*>(orow + c0 + 8 * g) =
+                            make_uint4(pack_bf16x2(__uint_as_float(r[8 * g]) * inv, __uint_as_float(r[8 * g + 1]) * inv),
+                                       pack_bf16x2(__uint_as_float(r[8 * g + 2]) * inv, __uint_as_float(r[8 * g + 3]) * inv),
+                                       pack_bf16x2(__uint_as_float(r[8 * g + 4]) * inv, __uint_as_float(r[8 * g + 5]) * inv),
+                                       pack_bf16x2(__uint_as_float(r[8 * g + 6]) * inv, __uint_as_float(r[8 * g + 7]) * inv));
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(o_empty);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
+}
+
 // fp32 [rows, cols] (ld) -> bf16 [rows, cols_pad] zero-padded (GEMM A operands that are not
 // produced in bf16 by their own kernel)
 __global__ void cast_pad_bf16_kernel(const float* __restrict__ src, int ld_src, __nv_bfloat16* dst, int ld_dst, int rows, int cols) {
@@ -312,6 +561,7 @@ struct Bf16Weights {
     __nv_bfloat16* tok_lp = nullptr; // [rows, feat0 K padded] bf16 copy of tok_feat (feat_0 GEMM A operand)
     int feat0_kpad = 0;
     CUtensorMap tm_ln, tm_hin, tm_b, tm_tok;      // A-operand maps over the pass workspace
+    CUtensorMap tm_qkv;                           // q|k|v tiles for the attention kernel
 };
 
 }  // namespace srhep

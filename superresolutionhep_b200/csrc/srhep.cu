@@ -477,7 +477,10 @@ int alloc_workspace(SrhepHandle* h) {
     if ((rc = re(h->h1buf, R * d.head_h1 * sizeof(float)))) return rc;
     if ((rc = re(h->act_a, R * wide * 4))) return rc;
     if ((rc = re(h->act_b, R * std::max(d.h_dim, d.mlp_hid) * es))) return rc;
-    if (h->precision == SRHEP_PREC_BF16) { if ((rc = re(h->qkv_lp, R * 3 * d.h_dim * 2))) return rc; }
+    if (h->precision == SRHEP_PREC_BF16) {
+        if ((rc = re(h->qkv_lp, R * 3 * d.h_dim * 2))) return rc;
+        CK(h, cudaMemset(h->qkv_lp, 0, R * 3 * d.h_dim * 2));    // rows past a pass's end are read (masked) by the attention tiles: keep them finite
+    }
     else { if ((rc = re(h->qkv, R * 3 * d.h_dim * sizeof(float)))) return rc; }
     h->cap_ws_rows = R;
     return 0;
