@@ -97,9 +97,10 @@ int bf16_pack_weights(SrhepHandle* h, const float* wh) {
     memcpy(&b[bw.bias_head1], wh + L.h1.b, d.head_h1 * sizeof(float));
     CK(h, cudaMalloc(&bw.bias, b.size() * sizeof(float)));
     CK(h, cudaMemcpy(bw.bias, b.data(), b.size() * sizeof(float), cudaMemcpyHostToDevice));
-    CK(h, cudaFuncSetAttribute(gemm_bf16_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_bf16_smem_bytes<256>(4)));
+    CK(h, cudaFuncSetAttribute(gemm_bf16_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_bf16_smem_bytes<256>(4)));
+    CK(h, cudaFuncSetAttribute(gemm_bf16_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_bf16_smem_bytes<256>(4)));
     CK(h, cudaFuncSetAttribute(attn_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmemBytes));
-    CK(h, cudaFuncSetAttribute(gemm_bf16_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_bf16_smem_bytes<128>(hk / 64)));
+    CK(h, cudaFuncSetAttribute(gemm_bf16_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_bf16_smem_bytes<128>(hk / 64)));
     return 0;
 }
 
@@ -125,9 +126,9 @@ int bf16_on_bind(SrhepHandle* h) {
     return 0;
 }
 
-int64_t default_pass_tokens(int precision) { return precision == SRHEP_PREC_BF16 ? 32768 : 65536; }
+int64_t default_pass_tokens(int precision) { return precision == SRHEP_PREC_BF16 ? (1 << 21) : (1 << 19); }
 
-template <int BN>
+template <int BN, bool kLN = false>
 void launch_gemm_bf16(Engine& E, const CUtensorMap& tm, int M, int K, int N, const uint8_t* w_img, void* C, int ldc, int out_bf16,
                       const GemmEpilogue& ep) {
     if (E.rc || M <= 0) return;
@@ -135,7 +136,7 @@ void launch_gemm_bf16(Engine& E, const CUtensorMap& tm, int M, int K, int N, con
     p.M = M; p.num_kb = K / 64; p.w_img = w_img; p.C = C; p.ldc = ldc; p.out_bf16 = out_bf16; p.ep = ep;
     const int m_tiles = (M + kGemmBM - 1) / kGemmBM, n_tiles = N / BN;
     dim3 grid(std::max(1, std::min(m_tiles, 148 / n_tiles)), n_tiles);
-    gemm_bf16_kernel<BN><<<grid, kGemmThreads, gemm_bf16_smem_bytes<BN>(p.num_kb), E.s>>>(tm, p);
+    gemm_bf16_kernel<BN, kLN><<<grid, kGemmThreads, gemm_bf16_smem_bytes<BN>(p.num_kb), E.s>>>(tm, p);
     E.check("gemm_bf16");
 }
 
@@ -167,15 +168,22 @@ void bf16_forward(Engine& E, const Pass& p, const int* rev) {
         cast_pad_bf16_kernel<<<grid, 256, 0, E.s>>>(h->tok_feat, ncol, bw.tok_lp, bw.feat0_kpad, M, ncol);
         E.check("cast_pad_bf16");
     }
+    // LayerNorm + adaLN modulate of the freshly produced residual row is fused into the epilogue of the GEMM
+    // that produces it: ln1 of layer l rides on feat_0 (l = 0) / the previous layer's MLP2, ln2 on the out-projection.
+    auto with_ln = [&](GemmEpilogue& ep, int layer, bool second) {
+        const Layout::Layer& y = L.layers[layer];
+        const float* ml = mod + (size_t)layer * 6 * H;
+        ep.ln_out = a; ep.ld_ln = H; ep.ld_lnmod = h->mod_width; ep.ln_second = second ? 1 : 0;
+        if (!second) { ep.ln_w = E.W(y.n1w); ep.ln_b = E.W(y.n1b); ep.ln_shift = ml; ep.ln_scale = ml + H; }
+        else { ep.ln_w = E.W(y.n2w); ep.ln_b = E.W(y.n2b); ep.ln_shift = ml + 3 * H; ep.ln_scale = ml + 4 * H; }
+    };
     { GemmEpilogue ep; ep.row_bias = h->f0bias; ep.ld_row_bias = H; ep.row_event = rev; ep.act = 1;
-      launch_gemm_bf16<256>(E, bw.tm_tok, M, bw.feat0_kpad, H, bw.img + bw.feat0, x, H, 0, ep); }
+      with_ln(ep, 0, false);
+      launch_gemm_bf16<256, true>(E, bw.tm_tok, M, bw.feat0_kpad, H, bw.img + bw.feat0, x, H, 0, ep); }
     E.tap(h->tap_feat0, x, M);
     for (int l = 0; l < d.layers; ++l) {
-        const Layout::Layer& y = L.layers[l];
         const float* ml = mod + (size_t)l * 6 * H;
         const float* bl = bw.bias + l * bw.bias_layer_stride;
-        E.cat = SRHEP_CAT_LN;
-        E.ln_mod<__nv_bfloat16>(x, M, H, E.W(y.n1w), E.W(y.n1b), ml, ml + H, rev, 0, a);
         E.cat = SRHEP_CAT_QKV;
         { GemmEpilogue ep; ep.bias = h->bqkv + (size_t)l * 3 * H;
           launch_gemm_bf16<256>(E, bw.tm_ln, M, H, 3 * H, bw.img + bw.qkv[l], qkv, 3 * H, 1, ep); }
@@ -184,15 +192,15 @@ void bf16_forward(Engine& E, const Pass& p, const int* rev) {
         else launch_attn_bf16(E, p, b);
         E.cat = SRHEP_CAT_OUT;
         { GemmEpilogue ep; ep.bias = bl; ep.gate = ml + 2 * H; ep.ld_gate = h->mod_width; ep.row_event = rev; ep.resid = x; ep.ld_resid = H;
-          launch_gemm_bf16<256>(E, bw.tm_b, M, H, H, bw.img + bw.out[l], x, H, 0, ep); }
-        E.cat = SRHEP_CAT_LN;
-        E.ln_mod<__nv_bfloat16>(x, M, H, E.W(y.n2w), E.W(y.n2b), ml + 3 * H, ml + 4 * H, rev, 1, a);
+          with_ln(ep, l, true);
+          launch_gemm_bf16<256, true>(E, bw.tm_b, M, H, H, bw.img + bw.out[l], x, H, 0, ep); }
         E.cat = SRHEP_CAT_MLP1;
         { GemmEpilogue ep; ep.bias = bl + H; ep.act = 1;
           launch_gemm_bf16<256>(E, bw.tm_ln, M, H, H, bw.img + bw.mlp1[l], b, H, 1, ep); }
         E.cat = SRHEP_CAT_MLP2;
         { GemmEpilogue ep; ep.bias = bl + 2 * H; ep.act = 1; ep.gate = ml + 5 * H; ep.ld_gate = h->mod_width; ep.row_event = rev; ep.resid = x; ep.ld_resid = H;
-          launch_gemm_bf16<256>(E, bw.tm_b, M, H, H, bw.img + bw.mlp2[l], x, H, 0, ep); }
+          if (l + 1 < d.layers) { with_ln(ep, l + 1, false); launch_gemm_bf16<256, true>(E, bw.tm_b, M, H, H, bw.img + bw.mlp2[l], x, H, 0, ep); }
+          else launch_gemm_bf16<256>(E, bw.tm_b, M, H, H, bw.img + bw.mlp2[l], x, H, 0, ep); }
         if (h->debug && h->tap_layers) E.tap(h->tap_layers + (size_t)l * h->cap_tap * H, x, M);
     }
     E.cat = SRHEP_CAT_HEAD;

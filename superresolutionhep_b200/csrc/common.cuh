@@ -58,6 +58,13 @@ struct GemmEpilogue {
     int          act         = 0;        // 0 none, 1 LeakyReLU(0.01)
     const float* gate        = nullptr;  int ld_gate = 0;
     const float* resid       = nullptr;  int ld_resid = 0;
+    // Optional fused LayerNorm of the produced row (tcgen05 GEMM with BN == row width only):
+    //   y = (LN(C_row) * ln_w + ln_b) * (1 + ln_scale[event]) + ln_shift[event];  if ln_second: y = LN(y)
+    // written as a 16-bit A operand for the next GEMM (diffusion_transformer.py:8-9,38-52; dense.py:62).
+    void*        ln_out      = nullptr;  int ld_ln = 0;
+    const float* ln_w        = nullptr;  const float* ln_b = nullptr;
+    const float* ln_shift    = nullptr;  const float* ln_scale = nullptr;  int ld_lnmod = 0;
+    int          ln_second   = 0;
 };
 
 }  // namespace srhep

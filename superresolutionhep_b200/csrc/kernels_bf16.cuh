@@ -102,6 +102,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// 32 registers per thread -> 32 lanes x 32 consecutive fp32 columns of TMEM
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+          "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+          "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+          "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float fast_exp2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 // UMMA shared-memory descriptor: K-major operand, 128-byte swizzle, 8-row groups 1024 B apart.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
@@ -110,6 +125,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+
+// 256-bit global accesses (sm_100: LDG/STG.256)
+__device__ __forceinline__ void ldg256(const float* p, float* d) {
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3]), "=f"(d[4]), "=f"(d[5]), "=f"(d[6]), "=f"(d[7]) : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint32_t* v) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -128,7 +154,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 constexpr int kGemmBM = 128;
 constexpr int kGemmBK = 64;
 constexpr int kGemmStages = 4;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;        // 2 + 8 epilogue warps
 
 struct GemmBf16Params {
     int M;                  // valid rows
@@ -140,10 +166,10 @@ struct GemmBf16Params {
 
 template <int BN>
 constexpr size_t gemm_bf16_smem_bytes(int num_kb) {
-    return 1024 /*alignment slack*/ + (size_t)num_kb * BN * 128 + (size_t)kGemmStages * kGemmBM * 128 + 256;
+    return 1024 /*alignment slack*/ + (size_t)num_kb * BN * 128 + (size_t)kGemmStages * kGemmBM * 128 + 256 /*barriers*/ + 8192 /*LN partial sums*/;
 }
 
-template <int BN>
+template <int BN, bool kLN = false>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, GemmBf16Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -156,6 +182,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
     uint64_t* t_full = w_full + 1;               // [2] accumulator ready   MMA -> epilogue
     uint64_t* t_empty = t_full + 2;              // [2] accumulator drained epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+    float2* ln_stat = reinterpret_cast<float2*>(bars + 32);          // [2 tile parities][2 passes][2 halves][128 rows]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tiles = (p.M + kGemmBM - 1) / kGemmBM;
@@ -166,7 +193,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
         prefetch_tmap(&tmap_a);
         for (int i = 0; i < kGemmStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         mbar_init(w_full, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 8); }
         mbar_fence_init();
     }
     if (warp == 1) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
@@ -218,23 +245,36 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
             }
         }
     } else {
-        const int q = warp & 3;                                     // TMEM lane quarter this warp may read
+        // 8 epilogue warps: TMEM lane quarter q (rows), column half hh.  One thread = half a row.
+        const int q = warp & 3, hh = (warp - 2) >> 2;
+        constexpr int HALF = BN / 2, NCH = HALF / 32;
         const GemmEpilogue& ep = p.ep;
+        const uint32_t t_lane = (uint32_t)(q * 32) << 16;
+        const int rt = q * 32 + lane;                                 // row inside the tile
         uint32_t tile_i = 0;
         for (int t = blockIdx.x; t < m_tiles; t += gridDim.x, ++tile_i) {
             const uint32_t a = tile_i & 1, aph = (tile_i >> 1) & 1;
-            mbar_wait(&t_full[a], aph);
-            tc_fence_after();
-            const int row = t * kGemmBM + q * 32 + lane;
+            const int row = t * kGemmBM + rt;
             const bool valid = row < p.M;
             const int evt = valid ? (ep.row_event ? ep.row_event[row] : row) : 0;
+            const int colh = n_tile * BN + hh * HALF;                 // first global column of this thread
+            const uint32_t t_col = tmem_base + t_lane + a * BN + hh * HALF;
+            const float* rs_ptr = ep.resid ? ep.resid + (size_t)row * ep.ld_resid + colh : nullptr;
+            float rs[32];                                             // residual chunk, prefetched one chunk ahead
+            if (rs_ptr && valid) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) ldg256(rs_ptr + j, &rs[j]);
+            }
+            mbar_wait(&t_full[a], aph);
+            tc_fence_after();
+            float ln_s1 = 0.f, ln_s2 = 0.f;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c = 0; c < NCH; ++c) {
                 uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * BN + c0, r);
+                tmem_ld32(t_col + c * 32, r);
                 tmem_ld_wait();
                 if (valid) {
-                    const int col0 = n_tile * BN + c0;
+                    const int col0 = colh + c * 32;
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -259,25 +299,98 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
                     }
                     if (ep.resid) {
                         const float* g = ep.gate + (size_t)evt * ep.ld_gate + col0;
-                        const float* rs = ep.resid + (size_t)row * ep.ld_resid + col0;
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
                             const float4 g4 = *reinterpret_cast<const float4*>(g + j);
-                            const float4 r4 = *reinterpret_cast<const float4*>(rs + j);
-                            v[j] = fmaf(g4.x, v[j], r4.x); v[j + 1] = fmaf(g4.y, v[j + 1], r4.y);
-                            v[j + 2] = fmaf(g4.z, v[j + 2], r4.z); v[j + 3] = fmaf(g4.w, v[j + 3], r4.w);
+                            v[j] = fmaf(g4.x, v[j], rs[j]); v[j + 1] = fmaf(g4.y, v[j + 1], rs[j + 1]);
+                            v[j + 2] = fmaf(g4.z, v[j + 2], rs[j + 2]); v[j + 3] = fmaf(g4.w, v[j + 3], rs[j + 3]);
+                        }
+                        if (c + 1 < NCH) {                            // next chunk's residual: in flight during this chunk's stores
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8) ldg256(rs_ptr + (c + 1) * 32 + j, &rs[j]);
                         }
                     }
                     if (p.out_bf16) {
-                        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col0);
+                        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col0;
+                        uint32_t pk[16];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            dst[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                                                pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+                        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+                        stg256(dst, &pk[0]); stg256(dst + 16, &pk[8]);
                     } else {
-                        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0);
+                        float* dst = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        for (int j = 0; j < 32; j += 8) stg256(dst + j, reinterpret_cast<const uint32_t*>(&v[j]));
+                    }
+                    if constexpr (kLN) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) { ln_s1 += v[j]; ln_s2 = fmaf(v[j], v[j], ln_s2); r[j] = __float_as_uint(v[j]); }
+                    }
+                }
+                if constexpr (kLN) tmem_st32(t_col + c * 32, r);      // keep the finished row on chip
+            }
+            if constexpr (kLN) {
+                // LayerNorm (+ affine + adaLN modulate [+ second LayerNorm]) of the finished rows, re-read from TMEM.
+                // A row is split over two threads (column halves): partial sums meet in shared memory.
+                tmem_st_wait();
+                float2* st1 = ln_stat + (tile_i & 1) * 512;           // [2 passes][2 halves][128 rows]
+                float2* st2 = st1 + 256;
+                st1[hh * 128 + rt] = make_float2(ln_s1, ln_s2);
+                named_bar_sync(1, 256);
+                const float2 o1 = st1[(hh ^ 1) * 128 + rt];
+                const float inv_n = 1.0f / (float)BN;
+                float mean = (ln_s1 + o1.x) * inv_n;
+                float rstd = rsqrtf(fmaxf((ln_s2 + o1.y) * inv_n - mean * mean, 0.f) + kLnEps);
+                const float* sh = ep.ln_shift + (size_t)evt * ep.ld_lnmod + hh * HALF;
+                const float* sc = ep.ln_scale + (size_t)evt * ep.ld_lnmod + hh * HALF;
+                const float* lw = ep.ln_w + hh * HALF;
+                const float* lb = ep.ln_b + hh * HALF;
+                if (ep.ln_second) {
+                    float t1 = 0.f, t2 = 0.f;
+#pragma unroll 1
+                    for (int c = 0; c < NCH; ++c) {
+                        uint32_t r[32];
+                        tmem_ld32(t_col + c * 32, r);
+                        tmem_ld_wait();
+                        if (valid) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                float y = fmaf((__uint_as_float(r[j]) - mean) * rstd, __ldg(lw + c * 32 + j), __ldg(lb + c * 32 + j));
+                                y = fmaf(y, 1.f + sc[c * 32 + j], sh[c * 32 + j]);
+                                t1 += y; t2 = fmaf(y, y, t2);
+                                r[j] = __float_as_uint(y);
+                            }
+                        }
+                        tmem_st32(t_col + c * 32, r);
+                    }
+                    tmem_st_wait();
+                    st2[hh * 128 + rt] = make_float2(t1, t2);
+                    named_bar_sync(1, 256);
+                    const float2 o2 = st2[(hh ^ 1) * 128 + rt];
+                    mean = (t1 + o2.x) * inv_n;
+                    rstd = rsqrtf(fmaxf((t2 + o2.y) * inv_n - mean * mean, 0.f) + kLnEps);
+                }
+#pragma unroll 1
+                for (int c = 0; c < NCH; ++c) {
+                    uint32_t r[32];
+                    tmem_ld32(t_col + c * 32, r);
+                    tmem_ld_wait();
+                    if (valid) {
+                        float y[32];
+                        if (ep.ln_second) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) y[j] = (__uint_as_float(r[j]) - mean) * rstd;
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const float tt = fmaf((__uint_as_float(r[j]) - mean) * rstd, __ldg(lw + c * 32 + j), __ldg(lb + c * 32 + j));
+                                y[j] = fmaf(tt, 1.f + sc[c * 32 + j], sh[c * 32 + j]);
+                            }
+                        }
+                        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(ep.ln_out) + (size_t)row * ep.ld_ln + hh * HALF + c * 32;
+                        uint32_t pk[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(y[2 * j], y[2 * j + 1]);
+                        stg256(dst, &pk[0]); stg256(dst + 16, &pk[8]);
                     }
                 }
             }
@@ -291,21 +404,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
 }
 
-
-// 32 registers per thread -> 32 lanes x 32 consecutive fp32 columns of TMEM
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-          "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
-          "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
-          "r"(r[30]), "r"(r[31])
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ float fast_exp2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 // UMMA descriptor for an MN-major operand stored as [k rows][64 elements = 128 B], 128-byte
 // swizzle (8 k-rows per 1024-byte atom): V as the B operand of P.V, straight from its

@@ -120,7 +120,7 @@ struct SrhepHandle {
     int* cu_dev = nullptr; int* row_event = nullptr;
     int *chunk_event = nullptr, *chunk_row = nullptr, *chunk_len = nullptr, *ev_chunk_start = nullptr;
     AttnWork* attn_work = nullptr;
-    size_t cap_events = 0, cap_rows = 0, cap_chunks = 0, cap_work = 0;
+    size_t cap_events = 0, cap_rows = 0, cap_chunks = 0, cap_work = 0, cap_event_bufs = 0;
 
     // per-event buffers [B, .]
     float *temb = nullptr, *ev_a = nullptr, *ev_stats = nullptr, *layer_out = nullptr, *ctx = nullptr, *silu_ctx = nullptr;
@@ -447,7 +447,8 @@ int alloc_for_binding(SrhepHandle* h) {
     const SrhepDims& d = h->d;
     const size_t B = std::max(h->B, 1);
     int rc;
-    if ((rc = ensure(h, h->cu_dev, h->cap_events, B + 1))) return rc;   // cap_events tracks cu_dev only
+    if ((rc = ensure(h, h->cu_dev, h->cap_events, B + 1))) return rc;
+    if (B <= h->cap_event_bufs) return 0;                  // per-event buffers only ever grow
     if ((rc = dev_alloc(h, h->temb, B * d.t_emb))) return rc;
     if ((rc = dev_alloc(h, h->ev_a, B * 3 * kMaxHid))) return rc;
     if ((rc = dev_alloc(h, h->ev_stats, B * 2))) return rc;
@@ -457,13 +458,16 @@ int alloc_for_binding(SrhepHandle* h) {
     if ((rc = dev_alloc(h, h->mod, B * h->mod_width))) return rc;
     if ((rc = dev_alloc(h, h->f0bias, B * d.h_dim))) return rc;
     if ((rc = dev_alloc(h, h->t_fill, B))) return rc;
+    if ((rc = dev_alloc(h, h->ev_chunk_start, B + 1))) return rc;
+    h->cap_event_bufs = B;
     return 0;
 }
 
 int alloc_workspace(SrhepHandle* h) {
     const SrhepDims& d = h->d;
-    const size_t R = std::max(h->max_pass_rows, 1);
+    size_t R = std::max(h->max_pass_rows, 1);
     if (R <= h->cap_ws_rows) return 0;
+    R = (R + 4095) / 4096 * 4096;
     int rc;
     const size_t es = act_elem_size(h);
     const size_t wide = std::max<size_t>(d.v_in + d.ctx, std::max(d.h_dim, d.mlp_hid));
@@ -483,6 +487,7 @@ int alloc_workspace(SrhepHandle* h) {
     }
     else { if ((rc = re(h->qkv, R * 3 * d.h_dim * sizeof(float)))) return rc; }
     h->cap_ws_rows = R;
+    if (h->precision == SRHEP_PREC_BF16 && (rc = bf16_on_bind(h))) return rc;     // tensor maps follow the workspace
     return 0;
 }
 
@@ -758,11 +763,8 @@ int srhep_bind_events(SrhepHandle* h, const SrhepCond* c, const int32_t* cu, int
         CK(h, cudaMalloc(&h->partial, std::max<size_t>(nch, 1) * h->d.cond * sizeof(float)));
         h->cap_chunks = nch;
     }
-    if (h->ev_chunk_start) CK(h, cudaFree(h->ev_chunk_start)); h->ev_chunk_start = nullptr;
-    CK(h, cudaMalloc(&h->ev_chunk_start, (size_t)(B + 1) * sizeof(int)));
     if ((rc = ensure(h, h->attn_work, h->cap_work, work.size()))) return rc;
     if ((rc = alloc_workspace(h))) return rc;
-    if (h->precision == SRHEP_PREC_BF16 && (rc = bf16_on_bind(h))) return rc;
 
     CK(h, cudaMemcpyAsync(h->cu_dev, cu, (size_t)(B + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
     if (nch) {
