@@ -39,6 +39,8 @@ extern "C" {
  * accumulation; LayerNorm statistics, softmax, residual stream and ODE state stay fp32. */
 #define SRHEP_PREC_FP32 0
 #define SRHEP_PREC_BF16 1
+#define SRHEP_PREC_FP16 2   /* as BF16 but fp16 tcgen05 operands: same speed, 8x finer mantissa; activations behind a
+                             * LayerNorm and the weights are well inside fp16 range */
 
 /* fixed-grid solvers of torchdiffeq.odeint (call site models/flow_model.py:315-324) */
 #define SRHEP_EULER    0

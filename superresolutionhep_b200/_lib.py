@@ -11,7 +11,7 @@ from .config import SrDimsC
 _LIB: Optional[C.CDLL] = None
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsrhep.so")
 
-PREC_FP32, PREC_BF16 = 0, 1
+PREC_FP32, PREC_BF16, PREC_FP16 = 0, 1, 2
 METHODS = {"euler": 0, "midpoint": 1, "rk4": 2, "dopri5": 3}
 CATEGORIES = ("embed", "adaln", "feat0", "ln", "qkv", "attn", "out", "mlp1", "mlp2", "head")
 

@@ -24,12 +24,14 @@ int make_a_tmap(SrhepHandle* h, CUtensorMap* m, const void* base, uint64_t rows,
     cuuint64_t strides[1] = {ld * 2};
     cuuint32_t box[2] = {(cuuint32_t)kGemmBK, (cuuint32_t)kGemmBM};
     cuuint32_t es[2] = {1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = enc(m, (h->precision == SRHEP_PREC_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(h, SRHEP_E_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu", (int)r,
                                        (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld);
     return 0;
 }
+
+uint16_t f2h(float f) { const __half hv = __float2half_rn(f); uint16_t u; memcpy(&u, &hv, 2); return u; }
 
 uint16_t f2bf(float f) {
     uint32_t u; memcpy(&u, &f, 4);
@@ -39,7 +41,7 @@ uint16_t f2bf(float f) {
 }
 
 // W fp32 [N, K] (row pitch ldw) -> image [N / BN][kpad / 64][BN rows x 128 B], 128B-swizzled, K zero-padded
-void pack_weight(std::vector<uint8_t>& img, size_t off, const float* W, int ldw, int N, int K, int kpad, int BN) {
+void pack_weight(std::vector<uint8_t>& img, size_t off, const float* W, int ldw, int N, int K, int kpad, int BN, bool fp16) {
     const int nkb = kpad / 64;
     for (int n = 0; n < N; ++n) {
         const int nt = n / BN, nr = n % BN;
@@ -49,7 +51,7 @@ void pack_weight(std::vector<uint8_t>& img, size_t off, const float* W, int ldw,
                 uint16_t* dst = reinterpret_cast<uint16_t*>(row + ((c ^ (nr & 7)) * 16));
                 for (int j = 0; j < 8; ++j) {
                     const int k = kb * 64 + c * 8 + j;
-                    dst[j] = k < K ? f2bf(W[(size_t)n * ldw + k]) : (uint16_t)0;
+                    dst[j] = k < K ? (fp16 ? f2h(W[(size_t)n * ldw + k]) : f2bf(W[(size_t)n * ldw + k])) : (uint16_t)0;
                 }
             }
         }
@@ -72,16 +74,17 @@ int bf16_pack_weights(SrhepHandle* h, const float* wh) {
     const int hk = d.v_in + d.ctx;
     bw.head1 = take(d.head_h1, hk);
     std::vector<uint8_t> img(off);
-    pack_weight(img, bw.feat0, wh + L.feat0.w, L.feat0.in, H, ncol, bw.feat0_kpad, 256);
+    const bool fp16 = h->precision == SRHEP_PREC_FP16;
+    pack_weight(img, bw.feat0, wh + L.feat0.w, L.feat0.in, H, ncol, bw.feat0_kpad, 256, fp16);
     for (int l = 0; l < d.layers; ++l) {
         const Layout::Layer& y = L.layers[l];
         const Lin* qkv[3] = {&y.q, &y.k, &y.v};
-        for (int j = 0; j < 3; ++j) pack_weight(img, bw.qkv[l] + (size_t)j * H * H * 2, wh + qkv[j]->w, H, H, H, H, 256);
-        pack_weight(img, bw.out[l], wh + y.o.w, H, H, H, H, 256);
-        pack_weight(img, bw.mlp1[l], wh + y.m1.w, H, H, H, H, 256);
-        pack_weight(img, bw.mlp2[l], wh + y.m2.w, H, H, H, H, 256);
+        for (int j = 0; j < 3; ++j) pack_weight(img, bw.qkv[l] + (size_t)j * H * H * 2, wh + qkv[j]->w, H, H, H, H, 256, fp16);
+        pack_weight(img, bw.out[l], wh + y.o.w, H, H, H, H, 256, fp16);
+        pack_weight(img, bw.mlp1[l], wh + y.m1.w, H, H, H, H, 256, fp16);
+        pack_weight(img, bw.mlp2[l], wh + y.m2.w, H, H, H, H, 256, fp16);
     }
-    pack_weight(img, bw.head1, wh + L.h1.w, hk, d.head_h1, hk, hk, 128);
+    pack_weight(img, bw.head1, wh + L.h1.w, hk, d.head_h1, hk, hk, 128, fp16);
     CK(h, cudaMalloc(&bw.img, img.size()));
     CK(h, cudaMemcpy(bw.img, img.data(), img.size(), cudaMemcpyHostToDevice));
     bw.bytes = img.size();
@@ -126,7 +129,7 @@ int bf16_on_bind(SrhepHandle* h) {
     return 0;
 }
 
-int64_t default_pass_tokens(int precision) { return precision == SRHEP_PREC_BF16 ? (1 << 21) : (1 << 19); }
+int64_t default_pass_tokens(int precision) { return precision != SRHEP_PREC_FP32 ? (1 << 21) : (1 << 19); }
 
 template <int BN, bool kLN = false>
 void launch_gemm_bf16(Engine& E, const CUtensorMap& tm, int M, int K, int N, const uint8_t* w_img, void* C, int ldc, int out_bf16,
@@ -134,6 +137,7 @@ void launch_gemm_bf16(Engine& E, const CUtensorMap& tm, int M, int K, int N, con
     if (E.rc || M <= 0) return;
     GemmBf16Params p;
     p.M = M; p.num_kb = K / 64; p.w_img = w_img; p.C = C; p.ldc = ldc; p.out_bf16 = out_bf16; p.ep = ep;
+    p.fp16 = E.h->precision == SRHEP_PREC_FP16;
     const int m_tiles = (M + kGemmBM - 1) / kGemmBM, n_tiles = N / BN;
     dim3 grid(std::max(1, std::min(m_tiles, 148 / n_tiles)), n_tiles);
     gemm_bf16_kernel<BN, kLN><<<grid, kGemmThreads, gemm_bf16_smem_bytes<BN>(p.num_kb), E.s>>>(tm, p);
@@ -149,6 +153,7 @@ void launch_attn_bf16(Engine& E, const Pass& p, __nv_bfloat16* out) {
     q.items = reinterpret_cast<const AttnItem*>(h->attn_work + p.w0); q.n_items = p.w1 - p.w0;
     q.out = out; q.ldo = d.h_dim; q.h_dim = d.h_dim;
     q.scale_log2 = 1.4426950408889634f / sqrtf((float)(d.h_dim / d.heads));
+    q.fp16 = h->precision == SRHEP_PREC_FP16;
     dim3 grid(std::max(1, std::min(q.n_items, 2 * 148 / d.heads)), d.heads);
     attn_bf16_kernel<<<grid, kAttnThreads, kAttnSmemBytes, E.s>>>(h->bw.tm_qkv, q);
     E.check("attn_bf16");
@@ -158,6 +163,7 @@ void bf16_forward(Engine& E, const Pass& p, const int* rev) {
     SrhepHandle* h = E.h;
     const SrhepDims& d = h->d; const Layout& L = h->L; Bf16Weights& bw = h->bw;
     const int M = p.r1 - p.r0, H = d.h_dim, ncol = d.cond + d.noisy_out;
+    const int fp16 = h->precision == SRHEP_PREC_FP16;
     float* x = h->xres;
     const float* mod = h->mod;
     __nv_bfloat16* a = (__nv_bfloat16*)h->act_a; __nv_bfloat16* b = (__nv_bfloat16*)h->act_b;
@@ -165,7 +171,7 @@ void bf16_forward(Engine& E, const Pass& p, const int* rev) {
     E.cat = SRHEP_CAT_FEAT0;
     if (!E.rc) {
         const int grid = (int)std::min<size_t>(((size_t)M * bw.feat0_kpad + 255) / 256, 148 * 16);
-        cast_pad_bf16_kernel<<<grid, 256, 0, E.s>>>(h->tok_feat, ncol, bw.tok_lp, bw.feat0_kpad, M, ncol);
+        cast_pad_bf16_kernel<<<grid, 256, 0, E.s>>>(h->tok_feat, ncol, bw.tok_lp, bw.feat0_kpad, M, ncol, fp16);
         E.check("cast_pad_bf16");
     }
     // LayerNorm + adaLN modulate of the freshly produced residual row is fused into the epilogue of the GEMM
@@ -188,7 +194,7 @@ void bf16_forward(Engine& E, const Pass& p, const int* rev) {
         { GemmEpilogue ep; ep.bias = h->bqkv + (size_t)l * 3 * H;
           launch_gemm_bf16<256>(E, bw.tm_ln, M, H, 3 * H, bw.img + bw.qkv[l], qkv, 3 * H, 1, ep); }
         E.cat = SRHEP_CAT_ATTN;
-        if (getenv("SRHEP_ATTN_SIMT")) E.attention_simt<__nv_bfloat16>(p, qkv, b);
+        if (!fp16 && getenv("SRHEP_ATTN_SIMT")) E.attention_simt<__nv_bfloat16>(p, qkv, b);
         else launch_attn_bf16(E, p, b);
         E.cat = SRHEP_CAT_OUT;
         { GemmEpilogue ep; ep.bias = bl; ep.gate = ml + 2 * H; ep.ld_gate = h->mod_width; ep.row_event = rev; ep.resid = x; ep.ld_resid = H;
@@ -210,7 +216,8 @@ void bf16_forward(Engine& E, const Pass& p, const int* rev) {
         GemmEpilogue ep; ep.bias = E.W(L.h1.b); ep.act = 1;
         E.gemm_f32<float>((float*)h->act_a, hw, E.W(L.h1.w), hw, h->h1buf, d.head_h1, M, d.head_h1, hw, ep);
     } else {
-    E.head_prep<__nv_bfloat16>(E.head_params(p, x), a, hw);
+    if (fp16) E.head_prep<__half>(E.head_params(p, x), (__half*)a, hw);
+    else E.head_prep<__nv_bfloat16>(E.head_params(p, x), a, hw);
     { GemmEpilogue ep; ep.bias = bw.bias + bw.bias_head1; ep.act = 1;
       launch_gemm_bf16<128>(E, bw.tm_hin, M, hw, d.head_h1, bw.img + bw.head1, h->h1buf, d.head_h1, 0, ep); }
     }

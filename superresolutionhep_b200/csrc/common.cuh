@@ -1,6 +1,7 @@
 // Shared device helpers and parameter structs for the srhep sm_100a kernels.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>

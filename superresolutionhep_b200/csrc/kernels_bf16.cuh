@@ -9,6 +9,7 @@
 // memory descriptor with layout_type = SWIZZLE_128B, SBO = 1024 expects.
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -125,6 +126,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// same with fp16 operands (a_format = b_format = 0)
+__host__ __device__ constexpr uint32_t umma_idesc_16(int M, int N, int fp16) {
+    return fp16 ? (umma_idesc_bf16(M, N) & ~((7u << 7) | (7u << 10))) : umma_idesc_bf16(M, N);
+}
 
 // 256-bit global accesses (sm_100: LDG/STG.256)
 __device__ __forceinline__ void ldg256(const float* p, float* d) {
@@ -140,6 +145,11 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volat
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
+}
+// two fp32 -> packed 16-bit pair in the handle's operand format (0 = bf16, 1 = fp16)
+__device__ __forceinline__ uint32_t pack16(float lo, float hi, int fp16) {
+    if (fp16) { __half2 v = __floats2half2_rn(lo, hi); return *reinterpret_cast<uint32_t*>(&v); }
+    return pack_bf16x2(lo, hi);
 }
 
 // ------------------------------------------------------------------------------------
@@ -160,7 +170,8 @@ struct GemmBf16Params {
     int M;                  // valid rows
     int num_kb;             // K / 64 (K is zero-padded to a multiple of 64 in A and W)
     const uint8_t* w_img;   // [N / BN][num_kb][BN x 128 B] pre-swizzled bf16 weights
-    void* C; int ldc; int out_bf16;
+    void* C; int ldc; int out_bf16;   // out_bf16: C is 16-bit (operand format) instead of fp32
+    int fp16;               // operand / 16-bit output format: 0 = bf16, 1 = fp16
     GemmEpilogue ep;
 };
 
@@ -220,7 +231,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
             }
         }
     } else if (warp == 1) {
-        constexpr uint32_t idesc = umma_idesc_bf16(kGemmBM, BN);
+        const uint32_t idesc = umma_idesc_16(kGemmBM, BN, p.fp16);
         mbar_wait(w_full, 0);
         uint32_t it = 0, tile_i = 0;
         for (int t = blockIdx.x; t < m_tiles; t += gridDim.x, ++tile_i) {
@@ -314,7 +325,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
                         __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col0;
                         uint32_t pk[16];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+                        for (int j = 0; j < 16; ++j) pk[j] = pack16(v[2 * j], v[2 * j + 1], p.fp16);
                         stg256(dst, &pk[0]); stg256(dst + 16, &pk[8]);
                     } else {
                         float* dst = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
@@ -389,7 +400,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
                         __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(ep.ln_out) + (size_t)row * ep.ld_ln + hh * HALF + c * 32;
                         uint32_t pk[16];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(y[2 * j], y[2 * j + 1]);
+                        for (int j = 0; j < 16; ++j) pk[j] = pack16(y[2 * j], y[2 * j + 1], p.fp16);
                         stg256(dst, &pk[0]); stg256(dst + 16, &pk[8]);
                     }
                 }
@@ -437,6 +448,7 @@ struct AttnBf16Params {
     __nv_bfloat16* out; int ldo;      // [rows, h_dim]
     int h_dim;                        // column offsets: q = head*64, k = h_dim + head*64, v = 2*h_dim + head*64
     float scale_log2;                 // log2(e) / sqrt(head_dim)
+    int fp16;                         // 0 = bf16, 1 = fp16 operands / output
 };
 
 __global__ void __launch_bounds__(kAttnThreads, 2) attn_bf16_kernel(const __grid_constant__ CUtensorMap tmap_qkv, AttnBf16Params p) {
@@ -495,8 +507,8 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_bf16_kernel(const __grid
             }
         }
     } else if (warp == 1) {
-        constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);          // S = Q K^T
-        constexpr uint32_t idesc_o = umma_idesc_bf16_bmn(128, 64);       // O = P V (V MN-major)
+        const uint32_t idesc_s = umma_idesc_16(128, 128, p.fp16);            // S = Q K^T
+        const uint32_t idesc_o = umma_idesc_16(128, 64, p.fp16) | (1u << 16); // O = P V (V MN-major)
         uint32_t it = 0, item_i = 0;
         for (int w = blockIdx.x; w < p.n_items; w += gridDim.x, ++item_i) {
             const AttnItem a = p.items[w];
@@ -583,8 +595,8 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_bf16_kernel(const __grid
                     for (int g = 0; g < 4; ++g) {
                         const int chunk = ((c0 & 63) >> 3) + g;
                         *reinterpret_cast<uint4*>(prow + ((chunk ^ (row & 7)) << 4)) =
-                            make_uint4(pack_bf16x2(pv[8 * g], pv[8 * g + 1]), pack_bf16x2(pv[8 * g + 2], pv[8 * g + 3]),
-                                       pack_bf16x2(pv[8 * g + 4], pv[8 * g + 5]), pack_bf16x2(pv[8 * g + 6], pv[8 * g + 7]));
+                            make_uint4(pack16(pv[8 * g], pv[8 * g + 1], p.fp16), pack16(pv[8 * g + 2], pv[8 * g + 3], p.fp16),
+                                       pack16(pv[8 * g + 4], pv[8 * g + 5], p.fp16), pack16(pv[8 * g + 6], pv[8 * g + 7], p.fp16));
                     }
                 }
                 tc_fence_before();
@@ -622,10 +634,10 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_bf16_kernel(const __grid
 #pragma unroll
                     for (int g = 0; g < 4; ++g)
                         *reinterpret_cast<uint4*>(orow + c0 + 8 * g) =
-                            make_uint4(pack_bf16x2(__uint_as_float(r[8 * g]) * inv, __uint_as_float(r[8 * g + 1]) * inv),
-                                       pack_bf16x2(__uint_as_float(r[8 * g + 2]) * inv, __uint_as_float(r[8 * g + 3]) * inv),
-                                       pack_bf16x2(__uint_as_float(r[8 * g + 4]) * inv, __uint_as_float(r[8 * g + 5]) * inv),
-                                       pack_bf16x2(__uint_as_float(r[8 * g + 6]) * inv, __uint_as_float(r[8 * g + 7]) * inv));
+                            make_uint4(pack16(__uint_as_float(r[8 * g]) * inv, __uint_as_float(r[8 * g + 1]) * inv, p.fp16),
+                                       pack16(__uint_as_float(r[8 * g + 2]) * inv, __uint_as_float(r[8 * g + 3]) * inv, p.fp16),
+                                       pack16(__uint_as_float(r[8 * g + 4]) * inv, __uint_as_float(r[8 * g + 5]) * inv, p.fp16),
+                                       pack16(__uint_as_float(r[8 * g + 6]) * inv, __uint_as_float(r[8 * g + 7]) * inv, p.fp16));
                 }
             }
             tc_fence_before();
@@ -640,11 +652,13 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_bf16_kernel(const __grid
 
 // fp32 [rows, cols] (ld) -> bf16 [rows, cols_pad] zero-padded (GEMM A operands that are not
 // produced in bf16 by their own kernel)
-__global__ void cast_pad_bf16_kernel(const float* __restrict__ src, int ld_src, __nv_bfloat16* dst, int ld_dst, int rows, int cols) {
+__global__ void cast_pad_bf16_kernel(const float* __restrict__ src, int ld_src, __nv_bfloat16* dst, int ld_dst, int rows, int cols, int fp16) {
     const size_t n = (size_t)rows * ld_dst;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int r = (int)(i / ld_dst), c = (int)(i % ld_dst);
-        dst[i] = __float2bfloat16_rn(c < cols ? src[(size_t)r * ld_src + c] : 0.f);
+        const float v = c < cols ? src[(size_t)r * ld_src + c] : 0.f;
+        if (fp16) reinterpret_cast<__half*>(dst)[i] = __float2half_rn(v);
+        else dst[i] = __float2bfloat16_rn(v);
     }
 }
 

@@ -29,6 +29,7 @@ struct EmbedNetDev {
 
 __device__ __forceinline__ void store_out(float* p, float v) { *p = v; }
 __device__ __forceinline__ void store_out(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+__device__ __forceinline__ void store_out(__half* p, float v) { *p = __float2half_rn(v); }
 
 // out_s[j] = act(sum_k W[j, k] * in_s[k] + bias[j]);  one warp per output row.
 // act: 0 none, 1 LeakyReLU, 2 SiLU.  Caller syncs before and after.

@@ -181,7 +181,8 @@ int dev_alloc(SrhepHandle* h, T*& p, size_t n) {
     return 0;
 }
 
-size_t act_elem_size(const SrhepHandle* h) { return h->precision == SRHEP_PREC_BF16 ? 2 : 4; }
+bool is_lp(const SrhepHandle* h) { return h->precision != SRHEP_PREC_FP32; }
+size_t act_elem_size(const SrhepHandle* h) { return is_lp(h) ? 2 : 4; }
 
 int validate_dims(const SrhepDims& d) {
     auto bad = [&](const char* m) { return fail(nullptr, SRHEP_E_INVALID, "unsupported dims: %s", m); };
@@ -302,7 +303,7 @@ struct Engine {
         const Layout& L = h->L;
         const int nE = p.e1 - p.e0, M = p.r1 - p.r0;
         if (nE <= 0) return;
-        const bool lp = h->precision == SRHEP_PREC_BF16;
+        const bool lp = is_lp(h);
         const int* rev = h->row_event + p.r0;
         const int ncol = d.cond + d.noisy_out;
 
@@ -481,13 +482,13 @@ int alloc_workspace(SrhepHandle* h) {
     if ((rc = re(h->h1buf, R * d.head_h1 * sizeof(float)))) return rc;
     if ((rc = re(h->act_a, R * wide * 4))) return rc;
     if ((rc = re(h->act_b, R * std::max(d.h_dim, d.mlp_hid) * es))) return rc;
-    if (h->precision == SRHEP_PREC_BF16) {
+    if (is_lp(h)) {
         if ((rc = re(h->qkv_lp, R * 3 * d.h_dim * 2))) return rc;
         CK(h, cudaMemset(h->qkv_lp, 0, R * 3 * d.h_dim * 2));    // rows past a pass's end are read (masked) by the attention tiles: keep them finite
     }
     else { if ((rc = re(h->qkv, R * 3 * d.h_dim * sizeof(float)))) return rc; }
     h->cap_ws_rows = R;
-    if (h->precision == SRHEP_PREC_BF16 && (rc = bf16_on_bind(h))) return rc;     // tensor maps follow the workspace
+    if (is_lp(h) && (rc = bf16_on_bind(h))) return rc;     // tensor maps follow the workspace
     return 0;
 }
 
@@ -594,7 +595,8 @@ uint64_t srhep_launch_count(const SrhepHandle* h) { return h ? h->launches : 0; 
 int srhep_create(int device, const SrhepDims* dims, const float* weights_host, size_t n_floats, int precision, SrhepHandle** out) {
     if (!dims || !weights_host || !out) return fail(nullptr, SRHEP_E_INVALID, "null argument");
     *out = nullptr;
-    if (precision != SRHEP_PREC_FP32 && precision != SRHEP_PREC_BF16) return fail(nullptr, SRHEP_E_INVALID, "precision must be SRHEP_PREC_FP32 or SRHEP_PREC_BF16");
+    if (precision != SRHEP_PREC_FP32 && precision != SRHEP_PREC_BF16 && precision != SRHEP_PREC_FP16)
+        return fail(nullptr, SRHEP_E_INVALID, "precision must be SRHEP_PREC_FP32, SRHEP_PREC_BF16 or SRHEP_PREC_FP16");
     int rc = validate_dims(*dims);
     if (rc) return rc;
     Layout L = make_layout(*dims);
@@ -660,7 +662,7 @@ int srhep_create(int device, const SrhepDims* dims, const float* weights_host, s
         CKC(cudaMalloc(&h->r1, r.size() * sizeof(float)));
         CKC(cudaMemcpy(h->r1, r.data(), r.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
-    if (precision == SRHEP_PREC_BF16) {
+    if (precision != SRHEP_PREC_FP32) {
         rc = bf16_pack_weights(h, weights_host);
         if (rc) return cleanup(rc);
     }

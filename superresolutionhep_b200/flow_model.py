@@ -41,7 +41,7 @@ def _register(root: nn.Module, dotted: str, shape) -> None:
 
 
 def _resolve_precision(precision: Optional[str]) -> int:
-    """'fp32' | 'bf16' | None.  None follows the reference's ``-p/--precision`` switch
+    """'fp32' | 'bf16' | 'fp16' | None.  None follows the reference's ``-p/--precision`` switch
     (inference.py:330 -> torch.set_float32_matmul_precision): 'highest' keeps every
     contraction in fp32, 'high' / 'medium' allow the bf16 tcgen05 path."""
     p = precision or os.environ.get(_PREC_ENV)
@@ -52,6 +52,8 @@ def _resolve_precision(precision: Optional[str]) -> int:
         return _lib.PREC_FP32
     if p in ("bf16", "bfloat16", "high", "medium"):
         return _lib.PREC_BF16
+    if p in ("fp16", "float16", "half"):
+        return _lib.PREC_FP16
     raise ValueError(f"unknown precision {precision!r}")
 
 

@@ -1,0 +1,123 @@
+"""GPU parity of the tensor-core (tcgen05) path against the fp32 golden vectors / oracle.
+
+Tolerance (BASELINE.json north_star "rtol 1e-2 bf16", made well-posed as SURVEY.md 0 requires):
+``rtol = 1e-2`` with ``atol = 1e-2 * max|ref|``.
+
+* fp16 operands (``precision="fp16"``): per-evaluation velocities AND trajectories meet it.
+* bf16 operands (``precision="bf16"``): final HR cell features after the ODE meet it; a single
+  velocity evaluation is limited by the 8-bit bf16 mantissa of the GEMM operands amplified by
+  the velocity head (measured rel-L2 1-2.2e-2 with the synthetic weights; PyTorch's own bf16
+  autocast of the reference is worse), so it is checked as rel-L2 <= 3e-2 and
+  max-abs <= 3e-2 * max|ref| and reported.
+Masks are bit-exact in every mode (they are passed through).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sr_oracle
+from superresolutionhep_b200 import FlowModel
+from superresolutionhep_b200.default_configs import flow_config
+from superresolutionhep_b200.synthetic import synthetic_events, synthetic_noise, synthetic_state_dict
+
+pytestmark = pytest.mark.gpu
+
+
+def to_dev(batch):
+    return {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items()}
+
+
+def make_model(kind, seed, precision):
+    cfg = flow_config(kind)
+    m = FlowModel(cfg, precision=precision)
+    sd = synthetic_state_dict(m.dims, seed=seed)
+    m.load_state_dict(sd)
+    return m.eval().cuda(), sd, sr_oracle.derive_dims(cfg)
+
+
+def rel_l2(a, b):
+    return float((a - b).norm() / b.norm())
+
+
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+@pytest.mark.parametrize("kind,counts", [
+    ("single_e", [4, 128, 132, 36, 260, 500]),
+    ("multipart", [16, 0, 304, 48, 1600, 3280, 16]),        # multi-tile attention, empty event, max length
+])
+def test_velocity_matches_oracle(precision, kind, counts):
+    m, sd, dims = make_model(kind, 21, precision)
+    batch = synthetic_events(kind, len(counts), seed=3, counts=np.array(counts))
+    x = synthetic_noise(batch, seed=4)
+    t = torch.linspace(0.0, 1.0, len(counts))
+    v = m(to_dev(batch), x.cuda(), t.cuda()).cpu()
+    keep = [i for i, c in enumerate(counts) if c > 0]
+    sub = {k: (val[keep] if torch.is_tensor(val) else val) for k, val in batch.items()}
+    with torch.no_grad():
+        ref = sr_oracle.flow_forward(sd, dims, sub, x[keep], t[keep])
+    mask = sub["q_mask"]
+    got, r = v[keep][mask], ref[mask]
+    scale = float(r.abs().max())
+    err, rl2 = float((got - r).abs().max()), rel_l2(got, r)
+    print(f"[{precision} {kind}] max|err| {err:.3e} ({err / scale:.2e} of max|ref|), rel-L2 {rl2:.3e}")
+    assert torch.isfinite(v).all()
+    if precision == "fp16":
+        torch.testing.assert_close(got, r, rtol=1e-2, atol=1e-2 * scale)
+    else:
+        assert rl2 <= 3e-2 and err <= 3e-2 * scale
+
+
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+def test_config1_trajectory_matches_golden(precision, golden_dir):
+    """64 single-electron events, Euler, n_steps = 25: final HR cell features within rtol 1e-2 /
+    atol 1e-2 max|ref| of the fp32 reference trajectory, in both 16-bit modes."""
+    g = torch.load(os.path.join(golden_dir, "sr_config1_single_e.pt"))
+    m, sd, dims = make_model("single_e", g["weight_seed"], precision)
+    batch = synthetic_events("single_e", g["n_events"], seed=g["event_seed"])
+    x0 = synthetic_noise(batch, seed=g["noise_seed"])
+    xs = m.generate_samples(to_dev(batch), n_steps=g["n_steps"], method="euler", ret_seq=True, x0=x0.cuda()).cpu()
+    mask = batch["q_mask"]
+    for name, got, ref in (("x_final", xs[-1][mask], g["euler"]["x_final"][mask]),
+                           ("x_mid", xs[g["n_steps"] // 2][mask], g["euler"]["x_mid"][mask])):
+        scale = float(ref.abs().max())
+        print(f"[{precision}] {name}: max|err| {float((got - ref).abs().max()):.3e}, max|ref| {scale:.3f}, rel-L2 {rel_l2(got, ref):.3e}")
+        torch.testing.assert_close(got, ref, rtol=1e-2, atol=1e-2 * scale)
+    assert torch.equal(xs[0], x0)
+
+
+def test_tensor_core_attention_matches_simt_attention():
+    """The tcgen05 attention kernel against the CUDA-core fp32-math attention on the same
+    bf16 q/k/v (ragged lengths incl. 1-cell events, exact multiples of 128, and 26 key tiles)."""
+    m, sd, dims = make_model("multipart", 5, "bf16")
+    counts = np.array([1, 128, 129, 256, 700, 3280, 16, 127])
+    batch = synthetic_events("multipart", len(counts), seed=8, counts=counts)
+    x = synthetic_noise(batch, seed=9)
+    t = torch.full((len(counts),), 0.4)
+    mask = batch["q_mask"]
+    v_tc = m(to_dev(batch), x.cuda(), t.cuda()).cpu()[mask]
+    os.environ["SRHEP_ATTN_SIMT"] = "1"
+    try:
+        v_simt = m(to_dev(batch), x.cuda(), t.cuda()).cpu()[mask]
+    finally:
+        del os.environ["SRHEP_ATTN_SIMT"]
+    scale = float(v_simt.abs().max())
+    print(f"tc vs simt attention: max|diff| {float((v_tc - v_simt).abs().max()):.3e} of {scale:.3f}")
+    torch.testing.assert_close(v_tc, v_simt, rtol=5e-3, atol=5e-3 * scale)
+
+
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+def test_sharding_and_passes_are_bit_exact(precision):
+    m, sd, dims = make_model("single_e", 29, precision)
+    batch = synthetic_events("single_e", 96, seed=1234)
+    x0 = synthetic_noise(batch, seed=0)
+    mask = batch["q_mask"]
+    whole = m.generate_samples(to_dev(batch), n_steps=3, method="midpoint", x0=x0.cuda()).cpu()
+    m.pass_tokens = 5000
+    cut = m.generate_samples(to_dev(batch), n_steps=3, method="midpoint", x0=x0.cuda()).cpu()
+    assert torch.equal(whole[mask], cut[mask])
+    m.pass_tokens = 0
+    for sl in (slice(0, 40), slice(40, 96)):
+        sub = {k: (v[sl] if torch.is_tensor(v) else v) for k, v in batch.items()}
+        part = m.generate_samples(to_dev(sub), n_steps=3, method="midpoint", x0=x0[sl].cuda()).cpu()
+        assert torch.equal(part[mask[sl]], whole[sl][mask[sl]])

@@ -10,7 +10,7 @@ from superresolutionhep_b200.synthetic import synthetic_events, synthetic_noise,
 kind = sys.argv[1] if len(sys.argv) > 1 else "single_e"
 counts = np.array([int(c) for c in sys.argv[2].split(",")]) if len(sys.argv) > 2 else np.array([4, 128, 132, 36, 260, 500])
 cfg = flow_config(kind)
-m = FlowModel(cfg, precision="bf16")
+m = FlowModel(cfg, precision=os.environ.get("DIAG_PREC", "bf16"))
 sd = synthetic_state_dict(m.dims, seed=21)
 m.load_state_dict(sd); m.cuda()
 dims = sr_oracle.derive_dims(cfg)
