@@ -88,7 +88,7 @@ int bf16_pack_weights(SrhepHandle* h, const float* wh) {
     CK(h, cudaMalloc(&bw.img, img.size()));
     CK(h, cudaMemcpy(bw.img, img.data(), img.size(), cudaMemcpyHostToDevice));
     bw.bytes = img.size();
-    bw.bias_layer_stride = 3 * (size_t)H;
+    bw.bias_layer_stride = 7 * (size_t)H;      // out.b | mlp1.b | mlp2.b | norm1.w | norm1.b | norm2.w | norm2.b
     bw.bias_head1 = bw.bias_layer_stride * d.layers;
     std::vector<float> b(bw.bias_head1 + d.head_h1);
     for (int l = 0; l < d.layers; ++l) {
@@ -96,6 +96,10 @@ int bf16_pack_weights(SrhepHandle* h, const float* wh) {
         memcpy(&b[l * bw.bias_layer_stride], wh + y.o.b, H * sizeof(float));
         memcpy(&b[l * bw.bias_layer_stride + H], wh + y.m1.b, H * sizeof(float));
         memcpy(&b[l * bw.bias_layer_stride + 2 * H], wh + y.m2.b, H * sizeof(float));
+        memcpy(&b[l * bw.bias_layer_stride + 3 * H], wh + y.n1w, H * sizeof(float));
+        memcpy(&b[l * bw.bias_layer_stride + 4 * H], wh + y.n1b, H * sizeof(float));
+        memcpy(&b[l * bw.bias_layer_stride + 5 * H], wh + y.n2w, H * sizeof(float));
+        memcpy(&b[l * bw.bias_layer_stride + 6 * H], wh + y.n2b, H * sizeof(float));
     }
     memcpy(&b[bw.bias_head1], wh + L.h1.b, d.head_h1 * sizeof(float));
     CK(h, cudaMalloc(&bw.bias, b.size() * sizeof(float)));
@@ -140,6 +144,7 @@ void launch_gemm_bf16(Engine& E, const CUtensorMap& tm, int M, int K, int N, con
     p.fp16 = E.h->precision == SRHEP_PREC_FP16;
     const int m_tiles = (M + kGemmBM - 1) / kGemmBM, n_tiles = N / BN;
     dim3 grid(std::max(1, std::min(m_tiles, 148 / n_tiles)), n_tiles);
+    static_assert(!kLN || BN == 256, "the fused LayerNorm epilogue maps 256 epilogue threads to 256 columns");
     gemm_bf16_kernel<BN, kLN><<<grid, kGemmThreads, gemm_bf16_smem_bytes<BN>(p.num_kb), E.s>>>(tm, p);
     E.check("gemm_bf16");
 }
@@ -177,11 +182,11 @@ void bf16_forward(Engine& E, const Pass& p, const int* rev) {
     // LayerNorm + adaLN modulate of the freshly produced residual row is fused into the epilogue of the GEMM
     // that produces it: ln1 of layer l rides on feat_0 (l = 0) / the previous layer's MLP2, ln2 on the out-projection.
     auto with_ln = [&](GemmEpilogue& ep, int layer, bool second) {
-        const Layout::Layer& y = L.layers[layer];
         const float* ml = mod + (size_t)layer * 6 * H;
+        const float* bl = bw.bias + layer * bw.bias_layer_stride;      // 16-byte aligned copies of the LayerNorm affine
         ep.ln_out = a; ep.ld_ln = H; ep.ld_lnmod = h->mod_width; ep.ln_second = second ? 1 : 0;
-        if (!second) { ep.ln_w = E.W(y.n1w); ep.ln_b = E.W(y.n1b); ep.ln_shift = ml; ep.ln_scale = ml + H; }
-        else { ep.ln_w = E.W(y.n2w); ep.ln_b = E.W(y.n2b); ep.ln_shift = ml + 3 * H; ep.ln_scale = ml + 4 * H; }
+        if (!second) { ep.ln_w = bl + 3 * H; ep.ln_b = bl + 4 * H; ep.ln_shift = ml; ep.ln_scale = ml + H; }
+        else { ep.ln_w = bl + 5 * H; ep.ln_b = bl + 6 * H; ep.ln_shift = ml + 3 * H; ep.ln_scale = ml + 4 * H; }
     };
     { GemmEpilogue ep; ep.row_bias = h->f0bias; ep.ld_row_bias = H; ep.row_event = rev; ep.act = 1;
       with_ln(ep, 0, false);
@@ -198,8 +203,14 @@ void bf16_forward(Engine& E, const Pass& p, const int* rev) {
         else launch_attn_bf16(E, p, b);
         E.cat = SRHEP_CAT_OUT;
         { GemmEpilogue ep; ep.bias = bl; ep.gate = ml + 2 * H; ep.ld_gate = h->mod_width; ep.row_event = rev; ep.resid = x; ep.ld_resid = H;
+          if (getenv("SRHEP_NO_LNFUSE")) {
+              launch_gemm_bf16<256>(E, bw.tm_b, M, H, H, bw.img + bw.out[l], x, H, 0, ep);
+              const Layout::Layer& y = L.layers[l];
+              E.cat = SRHEP_CAT_LN;
+              E.ln_mod<__nv_bfloat16>(x, M, H, E.W(y.n2w), E.W(y.n2b), ml + 3 * H, ml + 4 * H, rev, 1, a);
+          } else {
           with_ln(ep, l, true);
-          launch_gemm_bf16<256, true>(E, bw.tm_b, M, H, H, bw.img + bw.out[l], x, H, 0, ep); }
+          launch_gemm_bf16<256, true>(E, bw.tm_b, M, H, H, bw.img + bw.out[l], x, H, 0, ep); } }
         E.cat = SRHEP_CAT_MLP1;
         { GemmEpilogue ep; ep.bias = bl + H; ep.act = 1;
           launch_gemm_bf16<256>(E, bw.tm_ln, M, H, H, bw.img + bw.mlp1[l], b, H, 1, ep); }

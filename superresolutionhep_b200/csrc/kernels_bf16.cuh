@@ -140,6 +140,8 @@ __device__ __forceinline__ void stg256(void* p, const uint32_t* v) {
     asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                  ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
 }
+template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -164,7 +166,8 @@ __device__ __forceinline__ uint32_t pack16(float lo, float hi, int fp16) {
 constexpr int kGemmBM = 128;
 constexpr int kGemmBK = 64;
 constexpr int kGemmStages = 4;
-constexpr int kGemmThreads = 320;        // 2 + 8 epilogue warps
+constexpr int kGemmStageEv = 4;          // events per tile whose epilogue parameter rows are staged in shared memory
+constexpr int kGemmThreads = 384;        // warpgroup 0: TMA, MMA, 2 idle warps; warpgroups 1-2: epilogue
 
 struct GemmBf16Params {
     int M;                  // valid rows
@@ -177,7 +180,8 @@ struct GemmBf16Params {
 
 template <int BN>
 constexpr size_t gemm_bf16_smem_bytes(int num_kb) {
-    return 1024 /*alignment slack*/ + (size_t)num_kb * BN * 128 + (size_t)kGemmStages * kGemmBM * 128 + 256 /*barriers*/ + 8192 /*LN partial sums*/;
+    return 1024 /*alignment slack*/ + (size_t)num_kb * BN * 128 + (size_t)kGemmStages * kGemmBM * 128 + 256 /*barriers*/ + 8192 /*LN partial sums*/
+           + (size_t)kGemmStageEv * 4 * BN * sizeof(float) /*per-event epilogue rows*/;
 }
 
 template <int BN, bool kLN = false>
@@ -194,6 +198,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
     uint64_t* t_empty = t_full + 2;              // [2] accumulator drained epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
     float2* ln_stat = reinterpret_cast<float2*>(bars + 32);          // [2 tile parities][2 passes][2 halves][128 rows]
+    float* s_ev = reinterpret_cast<float*>(ln_stat + 1024);          // [kGemmStageEv][add | gate | lnA | lnB][BN]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tiles = (p.M + kGemmBM - 1) / kGemmBM;
@@ -212,7 +217,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-
+    // register budget: 128 x 56 + 256 x 224 = 64512 <= 64K; the epilogue keeps half a row (128 fp32) per thread
+    if (warp < 4) {
+    setmaxnreg_dec<56>();
     if (warp == 0) {
         if (lane == 0) {
             // weights: one bulk copy per k-block
@@ -255,9 +262,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
                 __syncwarp();
             }
         }
+    }
     } else {
+        setmaxnreg_inc<224>();
         // 8 epilogue warps: TMEM lane quarter q (rows), column half hh.  One thread = half a row.
-        const int q = warp & 3, hh = (warp - 2) >> 2;
+        const int q = warp & 3, hh = (warp - 4) >> 2;
         constexpr int HALF = BN / 2, NCH = HALF / 32;
         const GemmEpilogue& ep = p.ep;
         const uint32_t t_lane = (uint32_t)(q * 32) << 16;
@@ -271,143 +280,348 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
             const int colh = n_tile * BN + hh * HALF;                 // first global column of this thread
             const uint32_t t_col = tmem_base + t_lane + a * BN + hh * HALF;
             const float* rs_ptr = ep.resid ? ep.resid + (size_t)row * ep.ld_resid + colh : nullptr;
-            float rs[32];                                             // residual chunk, prefetched one chunk ahead
+            // Per-event epilogue rows of this tile, combined once per (event, column) and staged in shared memory:
+            //   add = bias + row_bias[e], gate[e], lnA = ln_w (1 + scale[e]), lnB = ln_b (1 + scale[e]) + shift[e]
+            bool staged = false;
+            int ev0 = 0;
+            if constexpr (kLN) {
+                const int last = min(t * kGemmBM + kGemmBM, p.M) - 1;
+                ev0 = ep.row_event ? ep.row_event[t * kGemmBM] : t * kGemmBM;
+                const int ne = (ep.row_event ? ep.row_event[last] : last) - ev0 + 1;
+                staged = ne <= kGemmStageEv;
+                named_bar_sync(1, 256);                                // readers of the previous tile's rows are done
+                if (staged) {
+                    const int col = (warp - 4) * 32 + lane;            // 256 epilogue threads <-> BN columns
+                    const float lw = __ldg(ep.ln_w + col), lb = __ldg(ep.ln_b + col);
+                    const float bs = ep.bias ? __ldg(ep.bias + col) : 0.f;
+                    for (int e = 0; e < ne; ++e) {
+                        const size_t ge = (size_t)(ev0 + e);
+                        const float sc1 = 1.f + ep.ln_scale[ge * ep.ld_lnmod + col];
+                        float* dstp = s_ev + e * 4 * BN + col;
+                        dstp[0] = bs + (ep.row_bias ? ep.row_bias[ge * ep.ld_row_bias + col] : 0.f);
+                        dstp[BN] = ep.gate ? ep.gate[ge * ep.ld_gate + col] : 0.f;
+                        dstp[2 * BN] = lw * sc1;
+                        dstp[3 * BN] = fmaf(lb, sc1, ep.ln_shift[ge * ep.ld_lnmod + col]);
+                    }
+                }
+            }
+            float rs[32];                                             // residual chunk, prefetched one chunk ahead (streaming variant)
+            uint32_t vr[kLN ? HALF : 1];                              // LayerNorm variant: the half row, starting as the residual
+            float* v = reinterpret_cast<float*>(vr);
             if (rs_ptr && valid) {
+                if constexpr (kLN) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 8) ldg256(rs_ptr + j, &rs[j]);
+                    for (int j = 0; j < HALF; j += 8) ldg256(rs_ptr + j, &v[j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) ldg256(rs_ptr + j, &rs[j]);
+                }
             }
             mbar_wait(&t_full[a], aph);
             tc_fence_after();
-            float ln_s1 = 0.f, ln_s2 = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < NCH; ++c) {
-                uint32_t r[32];
-                tmem_ld32(t_col + c * 32, r);
-                tmem_ld_wait();
-                if (valid) {
-                    const int col0 = colh + c * 32;
-                    float v[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                    if (ep.bias) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + j));
-                            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-                        }
-                    }
-                    if (ep.row_bias) {
-                        const float* rb = ep.row_bias + (size_t)evt * ep.ld_row_bias + col0;
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 b4 = *reinterpret_cast<const float4*>(rb + j);
-                            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-                        }
-                    }
-                    if (ep.act == 1) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = leaky_relu(v[j]);
-                    }
-                    if (ep.resid) {
-                        const float* g = ep.gate + (size_t)evt * ep.ld_gate + col0;
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 g4 = *reinterpret_cast<const float4*>(g + j);
-                            v[j] = fmaf(g4.x, v[j], rs[j]); v[j + 1] = fmaf(g4.y, v[j + 1], rs[j + 1]);
-                            v[j + 2] = fmaf(g4.z, v[j + 2], rs[j + 2]); v[j + 3] = fmaf(g4.w, v[j + 3], rs[j + 3]);
-                        }
-                        if (c + 1 < NCH) {                            // next chunk's residual: in flight during this chunk's stores
-#pragma unroll
-                            for (int j = 0; j < 32; j += 8) ldg256(rs_ptr + (c + 1) * 32 + j, &rs[j]);
-                        }
-                    }
-                    if (p.out_bf16) {
-                        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col0;
-                        uint32_t pk[16];
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) pk[j] = pack16(v[2 * j], v[2 * j + 1], p.fp16);
-                        stg256(dst, &pk[0]); stg256(dst + 16, &pk[8]);
-                    } else {
-                        float* dst = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8) stg256(dst + j, reinterpret_cast<const uint32_t*>(&v[j]));
-                    }
-                    if constexpr (kLN) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) { ln_s1 += v[j]; ln_s2 = fmaf(v[j], v[j], ln_s2); r[j] = __float_as_uint(v[j]); }
-                    }
-                }
-                if constexpr (kLN) tmem_st32(t_col + c * 32, r);      // keep the finished row on chip
-            }
             if constexpr (kLN) {
-                // LayerNorm (+ affine + adaLN modulate [+ second LayerNorm]) of the finished rows, re-read from TMEM.
-                // A row is split over two threads (column halves): partial sums meet in shared memory.
-                tmem_st_wait();
-                float2* st1 = ln_stat + (tile_i & 1) * 512;           // [2 passes][2 halves][128 rows]
-                float2* st2 = st1 + 256;
-                st1[hh * 128 + rt] = make_float2(ln_s1, ln_s2);
-                named_bar_sync(1, 256);
-                const float2 o1 = st1[(hh ^ 1) * 128 + rt];
-                const float inv_n = 1.0f / (float)BN;
-                float mean = (ln_s1 + o1.x) * inv_n;
-                float rstd = rsqrtf(fmaxf((ln_s2 + o1.y) * inv_n - mean * mean, 0.f) + kLnEps);
-                const float* sh = ep.ln_shift + (size_t)evt * ep.ld_lnmod + hh * HALF;
-                const float* sc = ep.ln_scale + (size_t)evt * ep.ld_lnmod + hh * HALF;
-                const float* lw = ep.ln_w + hh * HALF;
-                const float* lb = ep.ln_b + hh * HALF;
-                if (ep.ln_second) {
-                    float t1 = 0.f, t2 = 0.f;
-#pragma unroll 1
+                // The half row (HALF fp32 values) lives in registers: it starts as the residual (all of its loads
+                // were issued before the accumulator was ready, 512 B in flight per thread), the accumulator is
+                // streamed through it chunk by chunk, and both LayerNorm passes run out of registers.
+                named_bar_sync(1, 256);                                // staged rows visible
+                const float* se = s_ev + ((staged && valid) ? (evt - ev0) : 0) * 4 * BN + hh * HALF;
+                float s1 = 0.f, s2 = 0.f;
+                if (staged) {
+#pragma unroll
                     for (int c = 0; c < NCH; ++c) {
                         uint32_t r[32];
                         tmem_ld32(t_col + c * 32, r);
                         tmem_ld_wait();
+                        if (c == NCH - 1) {                           // accumulator fully read: hand it back to the MMA warp
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&t_empty[a]);
+                        }
                         if (valid) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                float y = fmaf((__uint_as_float(r[j]) - mean) * rstd, __ldg(lw + c * 32 + j), __ldg(lb + c * 32 + j));
-                                y = fmaf(y, 1.f + sc[c * 32 + j], sh[c * 32 + j]);
-                                t1 += y; t2 = fmaf(y, y, t2);
-                                r[j] = __float_as_uint(y);
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 a4 = *reinterpret_cast<const float4*>(se + c * 32 + j);
+                                const float4 g4 = *reinterpret_cast<const float4*>(se + BN + c * 32 + j);
+                                const float aa[4] = {a4.x, a4.y, a4.z, a4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    float w = __uint_as_float(r[j + u]) + aa[u];
+                                    if (ep.act == 1) w = leaky_relu(w);
+                                    if (ep.resid) w = fmaf(gg[u], w, v[c * 32 + j + u]);
+                                    v[c * 32 + j + u] = w; s1 += w; s2 = fmaf(w, w, s2);
+                                }
+                            }
+                            float* dst = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + colh + c * 32;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8) stg256(dst + j, &vr[c * 32 + j]);
+                        }
+                    }
+                } else {
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    const int col0 = colh + c * 32;
+                    uint32_t r[32];
+                    tmem_ld32(t_col + c * 32, r);
+                    tmem_ld_wait();
+                    if (c == NCH - 1) {                               // accumulator fully read: hand it back to the MMA warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&t_empty[a]);
+                    }
+                    if (valid) {
+                        float w[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) w[j] = __uint_as_float(r[j]);
+                        if (ep.bias) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + j));
+                                w[j] += b4.x; w[j + 1] += b4.y; w[j + 2] += b4.z; w[j + 3] += b4.w;
                             }
                         }
-                        tmem_st32(t_col + c * 32, r);
+                        if (ep.row_bias) {
+                            const float* rb = ep.row_bias + (size_t)evt * ep.ld_row_bias + col0;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 b4 = *reinterpret_cast<const float4*>(rb + j);
+                                w[j] += b4.x; w[j + 1] += b4.y; w[j + 2] += b4.z; w[j + 3] += b4.w;
+                            }
+                        }
+                        if (ep.act == 1) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) w[j] = leaky_relu(w[j]);
+                        }
+                        if (ep.resid) {
+                            const float* g = ep.gate + (size_t)evt * ep.ld_gate + col0;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 g4 = *reinterpret_cast<const float4*>(g + j);
+                                w[j] = fmaf(g4.x, w[j], v[c * 32 + j]); w[j + 1] = fmaf(g4.y, w[j + 1], v[c * 32 + j + 1]);
+                                w[j + 2] = fmaf(g4.z, w[j + 2], v[c * 32 + j + 2]); w[j + 3] = fmaf(g4.w, w[j + 3], v[c * 32 + j + 3]);
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) { v[c * 32 + j] = w[j]; s1 += w[j]; s2 = fmaf(w[j], w[j], s2); }
+                        float* dst = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) stg256(dst + j, &vr[c * 32 + j]);
                     }
-                    tmem_st_wait();
+                }
+                }
+                float2* st1 = ln_stat + (tile_i & 1) * 512;           // [2 passes][2 halves][128 rows]
+                float2* st2 = st1 + 256;
+                st1[hh * 128 + rt] = make_float2(s1, s2);
+                named_bar_sync(1, 256);
+                const float2 o1 = st1[(hh ^ 1) * 128 + rt];
+                const float inv_n = 1.0f / (float)BN;
+                float mean = (s1 + o1.x) * inv_n;
+                float rstd = rsqrtf(fmaxf((s2 + o1.y) * inv_n - mean * mean, 0.f) + kLnEps);
+                float t1 = 0.f, t2 = 0.f;
+                if (staged) {
+                    const float nmr = -mean * rstd;
+#pragma unroll
+                    for (int j = 0; j < HALF; j += 4) {               // affine + adaLN modulate, in place: y = xhat lnA + lnB
+                        const float4 a4 = *reinterpret_cast<const float4*>(se + 2 * BN + j);
+                        const float4 b4 = *reinterpret_cast<const float4*>(se + 3 * BN + j);
+                        const float aa[4] = {a4.x, a4.y, a4.z, a4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float y = fmaf(fmaf(__uint_as_float(vr[j + u]), rstd, nmr), aa[u], bb[u]);
+                            t1 += y; t2 = fmaf(y, y, t2);
+                            vr[j + u] = __float_as_uint(y);
+                        }
+                    }
+                } else {
+                const float* sh = ep.ln_shift + (size_t)evt * ep.ld_lnmod + hh * HALF;
+                const float* sc = ep.ln_scale + (size_t)evt * ep.ld_lnmod + hh * HALF;
+                const float* lw = ep.ln_w + hh * HALF;
+                const float* lb = ep.ln_b + hh * HALF;
+#pragma unroll
+                for (int j = 0; j < HALF; j += 4) {                   // affine + adaLN modulate, in place
+                    const float4 w4 = __ldg(reinterpret_cast<const float4*>(lw + j));
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(lb + j));
+                    const float4 s4 = *reinterpret_cast<const float4*>(sc + j);
+                    const float4 h4 = *reinterpret_cast<const float4*>(sh + j);
+                    const float ww[4] = {w4.x, w4.y, w4.z, w4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+                    const float ss[4] = {s4.x, s4.y, s4.z, s4.w}, hs[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        float y = fmaf((__uint_as_float(vr[j + u]) - mean) * rstd, ww[u], bb[u]);
+                        y = fmaf(y, 1.f + ss[u], hs[u]);
+                        t1 += y; t2 = fmaf(y, y, t2);
+                        vr[j + u] = __float_as_uint(y);
+                    }
+                }
+                }
+                if (ep.ln_second) {                                   // second, non-affine LayerNorm (dense.py:62)
                     st2[hh * 128 + rt] = make_float2(t1, t2);
                     named_bar_sync(1, 256);
                     const float2 o2 = st2[(hh ^ 1) * 128 + rt];
                     mean = (t1 + o2.x) * inv_n;
                     rstd = rsqrtf(fmaxf((t2 + o2.y) * inv_n - mean * mean, 0.f) + kLnEps);
+#pragma unroll
+                    for (int j = 0; j < HALF; ++j) vr[j] = __float_as_uint((__uint_as_float(vr[j]) - mean) * rstd);
                 }
+                if (valid) {
+                    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(ep.ln_out) + (size_t)row * ep.ld_ln + hh * HALF;
+#pragma unroll
+                    for (int j = 0; j < HALF; j += 16) {
+                        uint32_t pk[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) pk[u] = pack16(__uint_as_float(vr[j + 2 * u]), __uint_as_float(vr[j + 2 * u + 1]), p.fp16);
+                        stg256(dst + j, pk);
+                    }
+                }
+            } else {
+                float ln_s1 = 0.f, ln_s2 = 0.f;
 #pragma unroll 1
                 for (int c = 0; c < NCH; ++c) {
                     uint32_t r[32];
                     tmem_ld32(t_col + c * 32, r);
                     tmem_ld_wait();
                     if (valid) {
-                        float y[32];
-                        if (ep.ln_second) {
+                        const int col0 = colh + c * 32;
+                        float v[32];
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) y[j] = (__uint_as_float(r[j]) - mean) * rstd;
-                        } else {
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                        if (ep.bias) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                const float tt = fmaf((__uint_as_float(r[j]) - mean) * rstd, __ldg(lw + c * 32 + j), __ldg(lb + c * 32 + j));
-                                y[j] = fmaf(tt, 1.f + sc[c * 32 + j], sh[c * 32 + j]);
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + j));
+                                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
                             }
                         }
-                        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(ep.ln_out) + (size_t)row * ep.ld_ln + hh * HALF + c * 32;
-                        uint32_t pk[16];
+                        if (ep.row_bias) {
+                            const float* rb = ep.row_bias + (size_t)evt * ep.ld_row_bias + col0;
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) pk[j] = pack16(y[2 * j], y[2 * j + 1], p.fp16);
-                        stg256(dst, &pk[0]); stg256(dst + 16, &pk[8]);
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 b4 = *reinterpret_cast<const float4*>(rb + j);
+                                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                            }
+                        }
+                        if (ep.act == 1) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = leaky_relu(v[j]);
+                        }
+                        if (ep.resid) {
+                            const float* g = ep.gate + (size_t)evt * ep.ld_gate + col0;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 g4 = *reinterpret_cast<const float4*>(g + j);
+                                v[j] = fmaf(g4.x, v[j], rs[j]); v[j + 1] = fmaf(g4.y, v[j + 1], rs[j + 1]);
+                                v[j + 2] = fmaf(g4.z, v[j + 2], rs[j + 2]); v[j + 3] = fmaf(g4.w, v[j + 3], rs[j + 3]);
+                            }
+                            if (c + 1 < NCH) {                            // next chunk's residual: in flight during this chunk's stores
+#pragma unroll
+                                for (int j = 0; j < 32; j += 8) ldg256(rs_ptr + (c + 1) * 32 + j, &rs[j]);
+                            }
+                        }
+                        if (p.out_bf16) {
+                            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col0;
+                            uint32_t pk[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) pk[j] = pack16(v[2 * j], v[2 * j + 1], p.fp16);
+                            stg256(dst, &pk[0]); stg256(dst + 16, &pk[8]);
+                        } else {
+                            float* dst = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8) stg256(dst + j, reinterpret_cast<const uint32_t*>(&v[j]));
+                        }
+                        if constexpr (kLN) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) { ln_s1 += v[j]; ln_s2 = fmaf(v[j], v[j], ln_s2); r[j] = __float_as_uint(v[j]); }
+                        }
+                    }
+                    if constexpr (kLN) tmem_st32(t_col + c * 32, r);      // keep the finished row on chip
+                }
+                if constexpr (kLN) {
+                    // LayerNorm (+ affine + adaLN modulate [+ second LayerNorm]) of the finished rows, re-read from TMEM.
+                    // A row is split over two threads (column halves): partial sums meet in shared memory.
+                    tmem_st_wait();
+                    float2* st1 = ln_stat + (tile_i & 1) * 512;           // [2 passes][2 halves][128 rows]
+                    float2* st2 = st1 + 256;
+                    st1[hh * 128 + rt] = make_float2(ln_s1, ln_s2);
+                    named_bar_sync(1, 256);
+                    const float2 o1 = st1[(hh ^ 1) * 128 + rt];
+                    const float inv_n = 1.0f / (float)BN;
+                    float mean = (ln_s1 + o1.x) * inv_n;
+                    float rstd = rsqrtf(fmaxf((ln_s2 + o1.y) * inv_n - mean * mean, 0.f) + kLnEps);
+                    const float* sh = ep.ln_shift + (size_t)evt * ep.ld_lnmod + hh * HALF;
+                    const float* sc = ep.ln_scale + (size_t)evt * ep.ld_lnmod + hh * HALF;
+                    const float* lw = ep.ln_w + hh * HALF;
+                    const float* lb = ep.ln_b + hh * HALF;
+                    if (ep.ln_second) {
+                        float t1 = 0.f, t2 = 0.f;
+#pragma unroll 1
+                        for (int c = 0; c < NCH; ++c) {
+                            uint32_t r[32];
+                            tmem_ld32(t_col + c * 32, r);
+                            tmem_ld_wait();
+                            if (valid) {
+#pragma unroll
+                                for (int j = 0; j < 32; j += 4) {
+                                    const float4 w4 = __ldg(reinterpret_cast<const float4*>(lw + c * 32 + j));
+                                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(lb + c * 32 + j));
+                                    const float4 s4 = *reinterpret_cast<const float4*>(sc + c * 32 + j);
+                                    const float4 h4 = *reinterpret_cast<const float4*>(sh + c * 32 + j);
+                                    const float ww[4] = {w4.x, w4.y, w4.z, w4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+                                    const float ss[4] = {s4.x, s4.y, s4.z, s4.w}, hs[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+                                    for (int u = 0; u < 4; ++u) {
+                                        float y = fmaf((__uint_as_float(r[j + u]) - mean) * rstd, ww[u], bb[u]);
+                                        y = fmaf(y, 1.f + ss[u], hs[u]);
+                                        t1 += y; t2 = fmaf(y, y, t2);
+                                        r[j + u] = __float_as_uint(y);
+                                    }
+                                }
+                            }
+                            tmem_st32(t_col + c * 32, r);
+                        }
+                        tmem_st_wait();
+                        st2[hh * 128 + rt] = make_float2(t1, t2);
+                        named_bar_sync(1, 256);
+                        const float2 o2 = st2[(hh ^ 1) * 128 + rt];
+                        mean = (t1 + o2.x) * inv_n;
+                        rstd = rsqrtf(fmaxf((t2 + o2.y) * inv_n - mean * mean, 0.f) + kLnEps);
+                    }
+#pragma unroll 1
+                    for (int c = 0; c < NCH; ++c) {
+                        uint32_t r[32];
+                        tmem_ld32(t_col + c * 32, r);
+                        tmem_ld_wait();
+                        if (valid) {
+                            float y[32];
+                            if (ep.ln_second) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) y[j] = (__uint_as_float(r[j]) - mean) * rstd;
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; j += 4) {
+                                    const float4 w4 = __ldg(reinterpret_cast<const float4*>(lw + c * 32 + j));
+                                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(lb + c * 32 + j));
+                                    const float4 s4 = *reinterpret_cast<const float4*>(sc + c * 32 + j);
+                                    const float4 h4 = *reinterpret_cast<const float4*>(sh + c * 32 + j);
+                                    const float ww[4] = {w4.x, w4.y, w4.z, w4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+                                    const float ss[4] = {s4.x, s4.y, s4.z, s4.w}, hs[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+                                    for (int u = 0; u < 4; ++u) {
+                                        const float tt = fmaf((__uint_as_float(r[j + u]) - mean) * rstd, ww[u], bb[u]);
+                                        y[j + u] = fmaf(tt, 1.f + ss[u], hs[u]);
+                                    }
+                                }
+                            }
+                            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(ep.ln_out) + (size_t)row * ep.ld_ln + hh * HALF + c * 32;
+                            uint32_t pk[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) pk[j] = pack16(y[2 * j], y[2 * j + 1], p.fp16);
+                            stg256(dst, &pk[0]); stg256(dst + 16, &pk[8]);
+                        }
                     }
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&t_empty[a]);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&t_empty[a]);
         }
     }
     tc_fence_before();
