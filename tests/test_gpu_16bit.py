@@ -103,7 +103,8 @@ def test_tensor_core_attention_matches_simt_attention():
         del os.environ["SRHEP_ATTN_SIMT"]
     scale = float(v_simt.abs().max())
     print(f"tc vs simt attention: max|diff| {float((v_tc - v_simt).abs().max()):.3e} of {scale:.3f}")
-    torch.testing.assert_close(v_tc, v_simt, rtol=5e-3, atol=5e-3 * scale)
+    # P is rounded to 16 bits before P.V on the tensor-core path (fp32 on the SIMT path): the stated 16-bit tolerance applies
+    torch.testing.assert_close(v_tc, v_simt, rtol=1e-2, atol=1e-2 * scale)
 
 
 @pytest.mark.parametrize("precision", ["fp16", "bf16"])
