@@ -304,9 +304,12 @@ def main():
         per_cat = {c: {"ms": float(ms_cat[i]), "launches": int(n_cat[i])} for i, c in enumerate(_lib.CATEGORIES)}
         n = counts.astype(np.float64)
         H, L = model.dims.h_dim, model.dims.layers
+        unit = 2.0 * H * H * n.sum()                                     # one 256x256 Linear over every real cell
+        fused = per_cat.get("chain", {"launches": 0})["launches"] > 0   # layer chain kernel in use (kernels_chain.cuh)
         algo = {                                                         # algorithmic FLOPs of one evaluation per category (real cells only)
-            "qkv": 2.0 * 3 * H * H * n.sum() * L, "out": 2.0 * H * H * n.sum() * L, "mlp1": 2.0 * H * H * n.sum() * L,
-            "mlp2": 2.0 * H * H * n.sum() * L, "attn": 4.0 * H * (n * n).sum() * L,
+            "attn": 4.0 * H * (n * n).sum() * L,
+            "qkv": 3 * unit * (1 if fused else L), "out": 0.0 if fused else unit * L, "mlp1": 0.0 if fused else unit * L,
+            "mlp2": 0.0 if fused else unit * L, "chain": unit * (3 * L + 3 * (L - 1)) if fused else 0.0,
         }
         total_ms = sum(c["ms"] for c in per_cat.values())
         dom = max(algo, key=lambda c: per_cat[c]["ms"])

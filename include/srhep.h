@@ -138,7 +138,8 @@ int srhep_get_tap(SrhepHandle* h, const char* name, float* out_dev, size_t n_flo
 #define SRHEP_CAT_MLP1  7   /* layer MLP first Linear + LeakyReLU                       */
 #define SRHEP_CAT_MLP2  8   /* layer MLP second Linear + LeakyReLU + gate + residual    */
 #define SRHEP_CAT_HEAD  9   /* velocity head + ODE update                               */
-#define SRHEP_NCAT     10
+#define SRHEP_CAT_CHAIN 10  /* fused layer chain: out-proj .. MLP .. next layer's LN1 + q|k|v  */
+#define SRHEP_NCAT     11
 int srhep_profile(SrhepHandle* h, const float* x_dev, float t, float* v_dev, float* ms_by_cat,
                   int32_t* launches_by_cat, void* stream);
 

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsrhep.so
 
 PREC_FP32, PREC_BF16, PREC_FP16 = 0, 1, 2
 METHODS = {"euler": 0, "midpoint": 1, "rk4": 2, "dopri5": 3}
-CATEGORIES = ("embed", "adaln", "feat0", "ln", "qkv", "attn", "out", "mlp1", "mlp2", "head")
+CATEGORIES = ("embed", "adaln", "feat0", "ln", "qkv", "attn", "out", "mlp1", "mlp2", "head", "chain")
 
 # every symbol include/srhep.h declares
 EXPORTS = (

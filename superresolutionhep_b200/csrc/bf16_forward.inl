@@ -107,6 +107,8 @@ int bf16_pack_weights(SrhepHandle* h, const float* wh) {
     CK(h, cudaFuncSetAttribute(gemm_bf16_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_bf16_smem_bytes<256>(4)));
     CK(h, cudaFuncSetAttribute(gemm_bf16_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_bf16_smem_bytes<256>(4)));
     CK(h, cudaFuncSetAttribute(attn_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmemBytes));
+    CK(h, cudaFuncSetAttribute(layer_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemBytes));
+    CK(h, cudaFuncSetAttribute(layer_chain_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CK(h, cudaFuncSetAttribute(gemm_bf16_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_bf16_smem_bytes<128>(hk / 64)));
     return 0;
 }
@@ -164,6 +166,37 @@ void launch_attn_bf16(Engine& E, const Pass& p, __nv_bfloat16* out) {
     E.check("attn_bf16");
 }
 
+// One launch for the row-local part of DiT layer l: out-projection ... q|k|v of layer l + 1 (kernels_chain.cuh)
+void launch_chain(Engine& E, int M, int l, const int* rev) {
+    if (E.rc || M <= 0) return;
+    SrhepHandle* h = E.h;
+    const SrhepDims& d = h->d; Bf16Weights& bw = h->bw;
+    const int H = d.h_dim;
+    const bool last = l + 1 == d.layers;
+    const float* ml = h->mod + (size_t)l * 6 * H;
+    const float* bl = bw.bias + l * bw.bias_layer_stride;
+    ChainParams q{};
+    q.M = M; q.n_stages = last ? 3 : 6; q.fp16 = h->precision == SRHEP_PREC_FP16;
+    q.row_event = rev; q.x = h->xres;
+    q.w[0] = bw.img + bw.out[l]; q.w[1] = bw.img + bw.mlp1[l]; q.w[2] = bw.img + bw.mlp2[l];
+    q.bias[0] = bl; q.bias[1] = bl + H; q.bias[2] = bl + 2 * H;
+    q.gate_msa = ml + 2 * H; q.shift_mlp = ml + 3 * H; q.scale_mlp = ml + 4 * H; q.gate_mlp = ml + 5 * H;
+    q.ld_mod = h->mod_width;
+    q.ln2_w = bl + 5 * H; q.ln2_b = bl + 6 * H;
+    if (!last) {
+        const float* mn = h->mod + (size_t)(l + 1) * 6 * H;
+        const float* bn = bw.bias + (l + 1) * bw.bias_layer_stride;
+        for (int j = 0; j < 3; ++j) { q.w[3 + j] = bw.img + bw.qkv[l + 1] + (size_t)j * H * H * 2; q.bias[3 + j] = h->bqkv + ((size_t)(l + 1) * 3 + j) * H; }
+        q.shift_nxt = mn; q.scale_nxt = mn + H;
+        q.ln1_w = bn + 3 * H; q.ln1_b = bn + 4 * H;
+        q.qkv = h->qkv_lp;
+    }
+    const int m_tiles = (M + 127) / 128;
+    const int grid = std::max(1, std::min(m_tiles, 2 * 148));
+    layer_chain_kernel<<<grid, kChainThreads, kChainSmemBytes, E.s>>>(bw.tm_b, q);
+    E.check("layer_chain");
+}
+
 void bf16_forward(Engine& E, const Pass& p, const int* rev) {
     SrhepHandle* h = E.h;
     const SrhepDims& d = h->d; const Layout& L = h->L; Bf16Weights& bw = h->bw;
@@ -192,6 +225,21 @@ void bf16_forward(Engine& E, const Pass& p, const int* rev) {
       with_ln(ep, 0, false);
       launch_gemm_bf16<256, true>(E, bw.tm_tok, M, bw.feat0_kpad, H, bw.img + bw.feat0, x, H, 0, ep); }
     E.tap(h->tap_feat0, x, M);
+    const bool chain = (H == kChainH && d.mlp_hid == kChainH) && !getenv("SRHEP_NO_CHAIN");
+    if (chain) {
+        // layer 0's q|k|v come from the feat_0 GEMM's fused LN1; every later projection rides in the previous layer's chain kernel
+        E.cat = SRHEP_CAT_QKV;
+        { GemmEpilogue ep; ep.bias = h->bqkv;
+          launch_gemm_bf16<256>(E, bw.tm_ln, M, H, 3 * H, bw.img + bw.qkv[0], qkv, 3 * H, 1, ep); }
+        for (int l = 0; l < d.layers; ++l) {
+            E.cat = SRHEP_CAT_ATTN;
+            if (!fp16 && getenv("SRHEP_ATTN_SIMT")) E.attention_simt<__nv_bfloat16>(p, qkv, b);
+            else launch_attn_bf16(E, p, b);
+            E.cat = SRHEP_CAT_CHAIN;
+            launch_chain(E, M, l, rev);
+            if (h->debug && h->tap_layers) E.tap(h->tap_layers + (size_t)l * h->cap_tap * H, x, M);
+        }
+    } else
     for (int l = 0; l < d.layers; ++l) {
         const float* ml = mod + (size_t)l * 6 * H;
         const float* bl = bw.bias + l * bw.bias_layer_stride;

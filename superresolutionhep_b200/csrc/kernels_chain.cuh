@@ -1,0 +1,380 @@
+// Fused DiT-layer chain for sm_100a: everything between two attention calls that is local to a
+// cell (row), in ONE kernel per layer (models/diffusion_transformer.py:30-53, models/dense.py:49-83,
+// models/attention.py:112-123):
+//
+//   stage 0  out-projection of the attention output      x1 = x + gate_msa * (A Wo^T + bo)
+//            LN2(x1) * (1 + scale_mlp) + shift_mlp, then the Dense's own non-affine LN  -> A
+//   stage 1  MLP first Linear + LeakyReLU                                              -> A
+//   stage 2  MLP second Linear + LeakyReLU              x2 = x1 + gate_mlp * leaky(A W2^T + b2)
+//            LN1_{l+1}(x2) * (1 + scale_msa) + shift_msa  (next layer's attention input) -> A
+//   stage 3-5  Q, K, V projections of the NEXT layer                                   -> global (16 bit)
+//
+// A CTA owns one 128-row tile at a time.  The A operand (128 x 256, 16 bit, 64 KB, K-major with
+// 128-byte swizzle) is loaded once by TMA (the attention output) and then rewritten IN PLACE by the
+// epilogue of each stage; the six 256 x 256 weight matrices are streamed from L2 through a ring of
+// 16 KB slots (128 output rows x 64 k) by cp.async.bulk; the fp32 accumulator (128 lanes x 256
+// columns of TMEM) doubles as the parking place of the finished residual row between the
+// LayerNorm passes.  The activations of the tile never leave the SM between stages: per cell
+// and layer the kernel reads 512 B (attention output) + 1 KB (residual), writes 1 KB (residual) +
+// 1.5 KB (q|k|v) for 786 432 FLOP.  Two CTAs share an SM (2 x 112 KB of shared memory, 2 x 256
+// TMEM columns) so that one CTA's epilogue runs under the other's MMAs.
+//   warp 0: TMA producer   warp 1: TMEM allocator + MMA issuer   warps 2-9: epilogue (TMEM lane
+//   quarter = warp & 3, column half = (warp - 2) >> 2; one thread = half a row)
+#pragma once
+#include "kernels_bf16.cuh"
+
+namespace srhep {
+
+constexpr int kChainThreads = 320;
+constexpr int kChainSlots = 3;
+constexpr uint32_t kChainSlotBytes = 16384;          // 128 weight rows x 128 B
+constexpr uint32_t kChainABytes = 65536;             // 4 k-blocks x (128 rows x 128 B)
+constexpr size_t kChainSmemBytes = kChainABytes + kChainSlots * kChainSlotBytes + 128;
+constexpr int kChainH = 256;
+
+struct ChainParams {
+    int M;                       // rows of this pass
+    int n_stages;                // 6, or 3 for the last layer (no next attention)
+    int fp16;                    // 16-bit operand format: 0 = bf16, 1 = fp16
+    const int* row_event;        // [M] global event id of each row
+    float* x;                    // [M, 256] fp32 residual stream, updated in place
+    const uint8_t* w[6];         // pre-swizzled weight images [4 k-blocks][256 rows x 128 B]
+    const float* bias[6];        // [256] each
+    const float* gate_msa;       // per-event rows (stride ld_mod floats)
+    const float* shift_mlp; const float* scale_mlp; const float* gate_mlp;
+    const float* shift_nxt; const float* scale_nxt;       // next layer's shift_msa / scale_msa
+    int ld_mod;
+    const float* ln2_w; const float* ln2_b;                // this layer's norm2 affine
+    const float* ln1_w; const float* ln1_b;                // next layer's norm1 affine
+    void* qkv;                   // [M, 768] 16-bit q|k|v of the next layer
+};
+
+// acc + bias (+ LeakyReLU), gated into the residual: returns the new residual chunk in r[] (as bits)
+template <bool kAct>
+__device__ __forceinline__ void chain_resid_chunk(uint32_t (&r)[32], const float (&xr)[32], const float* __restrict__ bias,
+                                                  const float* __restrict__ gate, float& s1, float& s2) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + j));
+        const float4 g4 = *reinterpret_cast<const float4*>(gate + j);
+        const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float w = __uint_as_float(r[j + u]) + bb[u];
+            if (kAct) w = leaky_relu(w);
+            w = fmaf(gg[u], w, xr[j + u]);
+            s1 += w; s2 = fmaf(w, w, s2);
+            r[j + u] = __float_as_uint(w);
+        }
+    }
+}
+
+// 32 consecutive values of row `rt` -> 16-bit, into the K-major 128B-swizzled A buffer at columns [col0, col0 + 32)
+__device__ __forceinline__ void chain_store_a(uint8_t* s_a, int rt, int col0, const float (&v)[32], int fp16) {
+    uint8_t* arow = s_a + (col0 >> 6) * 16384 + rt * 128;
+    const int cb = (col0 & 63) >> 3;
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+        *reinterpret_cast<uint4*>(arow + (((cb + g) ^ (rt & 7)) << 4)) =
+            make_uint4(pack16(v[8 * g], v[8 * g + 1], fp16), pack16(v[8 * g + 2], v[8 * g + 3], fp16),
+                       pack16(v[8 * g + 4], v[8 * g + 5], fp16), pack16(v[8 * g + 6], v[8 * g + 7], fp16));
+}
+
+__global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __grid_constant__ CUtensorMap tmap_a, ChainParams p) {
+    extern __shared__ __align__(1024) uint8_t chain_smem[];      // no static smem in this kernel: the dynamic window starts 1024-aligned
+    uint8_t* s_a = chain_smem;
+    if ((smem_u32(s_a) & 1023u) != 0) __trap();
+    uint8_t* s_w = s_a + kChainABytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_w + kChainSlots * kChainSlotBytes);
+    uint64_t* a_full = bars;             // TMA -> MMA      attention-output tile landed
+    uint64_t* a_free = bars + 1;         // MMA -> TMA      last MMA of the tile retired: A may be overwritten
+    uint64_t* w_full = bars + 2;         // [slots] TMA -> MMA
+    uint64_t* w_empty = bars + 5;        // [slots] MMA -> TMA
+    uint64_t* acc_full = bars + 8;       // MMA -> epilogue  accumulator of a stage complete
+    uint64_t* epi_done = bars + 9;       // epilogue -> MMA  accumulator drained (and A rewritten)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tiles = (p.M + 127) / 128;
+    constexpr uint32_t kTmemCols = 256;
+    const int slots_per_tile = p.n_stages * 8;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_a);
+        mbar_init(a_full, 1); mbar_init(a_free, 1);
+        for (int i = 0; i < kChainSlots; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+        mbar_init(acc_full, 1); mbar_init(epi_done, 8);
+        mbar_fence_init();
+    }
+    if (warp == 1) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t slot_it = 0, tile_i = 0;
+            for (int t = blockIdx.x; t < m_tiles; t += gridDim.x, ++tile_i) {
+                for (int j = 0; j < slots_per_tile; ++j, ++slot_it) {
+                    if (j == (tile_i == 0 ? 0 : 2)) {                 // the A tile: first thing of the kernel, else after two weight slots of run-ahead
+                        if (tile_i > 0) mbar_wait(a_free, (tile_i - 1) & 1);
+                        mbar_expect_tx(a_full, kChainABytes);
+#pragma unroll
+                        for (int kb = 0; kb < 4; ++kb) tma_load_2d(s_a + kb * 16384, &tmap_a, a_full, kb * 64, t * 128);
+                    }
+                    const int g = j >> 3, kb = (j >> 1) & 3, nh = j & 1;
+                    const uint32_t s = slot_it % kChainSlots, ph = (slot_it / kChainSlots) & 1;
+                    mbar_wait(&w_empty[s], ph ^ 1);
+                    mbar_expect_tx(&w_full[s], kChainSlotBytes);
+                    bulk_load(s_w + s * kChainSlotBytes, p.w[g] + (size_t)(kb * 256 + nh * 128) * 128, kChainSlotBytes, &w_full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc = umma_idesc_16(128, 128, p.fp16);
+        uint32_t slot_it = 0, stage_it = 0, tile_i = 0;
+        for (int t = blockIdx.x; t < m_tiles; t += gridDim.x, ++tile_i) {
+            for (int g = 0; g < p.n_stages; ++g, ++stage_it) {
+                if (stage_it > 0) mbar_wait(epi_done, (stage_it - 1) & 1);      // accumulator drained, A operand of this stage in place
+                if (g == 0) mbar_wait(a_full, tile_i & 1);
+                tc_fence_after();
+                for (int j = 0; j < 8; ++j, ++slot_it) {
+                    const int kb = j >> 1, nh = j & 1;
+                    const uint32_t s = slot_it % kChainSlots, ph = (slot_it / kChainSlots) & 1;
+                    mbar_wait(&w_full[s], ph);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t a_addr = smem_u32(s_a + kb * 16384), b_addr = smem_u32(s_w + s * kChainSlotBytes);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(tmem_base + nh * 128, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                                      (uint32_t)((kb | k) != 0));
+                        tc_commit(&w_empty[s]);
+                        if (j == 7) {
+                            tc_commit(acc_full);
+                            if (g == p.n_stages - 1) tc_commit(a_free);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        const int q = warp & 3, hh = (warp - 2) >> 2;
+        const int rt = q * 32 + lane;                                  // row inside the tile = TMEM lane
+        const uint32_t t_col = tmem_base + ((uint32_t)(q * 32) << 16) + hh * 128;
+        float2* st1 = reinterpret_cast<float2*>(s_a);                  // LayerNorm partial sums: scratch inside the (then dead) A buffer
+        float2* st2 = st1 + 256;
+        const int fp16 = p.fp16;
+        uint32_t stage_it = 0;
+        auto stage_done = [&]() {
+            fence_async_smem();                                        // A stores -> visible to the tensor-core (async) proxy
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(epi_done);
+            ++stage_it;
+        };
+        for (int t = blockIdx.x; t < m_tiles; t += gridDim.x) {
+            const int row = t * 128 + rt;
+            const bool valid = row < p.M;
+            const int evt = valid ? p.row_event[row] : 0;
+            float* xrow = p.x + (size_t)row * kChainH + hh * 128;
+            const size_t eo = (size_t)evt * p.ld_mod + hh * 128;
+            constexpr float inv_n = 1.0f / (float)kChainH;
+
+            // ---------------------------------------------------------------- stage 0: out-projection, residual, LN2 + modulate + LN
+            {
+                float xr[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) xr[j] = 0.f;
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) ldg256(xrow + j, &xr[j]);            // in flight while the MMAs run
+                }
+                mbar_wait(acc_full, stage_it & 1);
+                tc_fence_after();
+                float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t r[32];
+                    tmem_ld32(t_col + c * 32, r);
+                    tmem_ld_wait();
+                    chain_resid_chunk<false>(r, xr, p.bias[0] + hh * 128 + c * 32, p.gate_msa + eo + c * 32, s1, s2);
+                    if (valid) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) stg256(xrow + c * 32 + j, &r[j]);
+                        if (c < 3) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8) ldg256(xrow + (c + 1) * 32 + j, &xr[j]);
+                        }
+                    }
+                    tmem_st32(t_col + c * 32, r);
+                }
+                tmem_st_wait();
+                st1[hh * 128 + rt] = make_float2(s1, s2);
+                named_bar_sync(1, 256);
+                const float2 o1 = st1[(hh ^ 1) * 128 + rt];
+                float mean = (s1 + o1.x) * inv_n;
+                float rstd = rsqrtf(fmaxf((s2 + o1.y) * inv_n - mean * mean, 0.f) + kLnEps);
+                float t1 = 0.f, t2 = 0.f;
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {                            // affine + adaLN modulate, parked back in TMEM
+                    uint32_t r[32];
+                    tmem_ld32(t_col + c * 32, r);
+                    tmem_ld_wait();
+                    const float* lw = p.ln2_w + hh * 128 + c * 32; const float* lb = p.ln2_b + hh * 128 + c * 32;
+                    const float* sc = p.scale_mlp + eo + c * 32; const float* sh = p.shift_mlp + eo + c * 32;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 w4 = __ldg(reinterpret_cast<const float4*>(lw + j)), b4 = __ldg(reinterpret_cast<const float4*>(lb + j));
+                        const float4 s4 = *reinterpret_cast<const float4*>(sc + j), h4 = *reinterpret_cast<const float4*>(sh + j);
+                        const float ww[4] = {w4.x, w4.y, w4.z, w4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+                        const float ss[4] = {s4.x, s4.y, s4.z, s4.w}, hs[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            float y = fmaf((__uint_as_float(r[j + u]) - mean) * rstd, ww[u], bb[u]);
+                            y = fmaf(y, 1.f + ss[u], hs[u]);
+                            t1 += y; t2 = fmaf(y, y, t2);
+                            r[j + u] = __float_as_uint(y);
+                        }
+                    }
+                    tmem_st32(t_col + c * 32, r);
+                }
+                tmem_st_wait();
+                st2[hh * 128 + rt] = make_float2(t1, t2);
+                named_bar_sync(1, 256);
+                const float2 o2 = st2[(hh ^ 1) * 128 + rt];
+                mean = (t1 + o2.x) * inv_n;
+                rstd = rsqrtf(fmaxf((t2 + o2.y) * inv_n - mean * mean, 0.f) + kLnEps);
+                named_bar_sync(1, 256);                                  // every thread has read its partner's sums: the scratch may be overwritten
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {                            // the Dense's own non-affine LayerNorm (models/dense.py:62) -> A
+                    uint32_t r[32];
+                    tmem_ld32(t_col + c * 32, r);
+                    tmem_ld_wait();
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = (__uint_as_float(r[j]) - mean) * rstd;
+                    chain_store_a(s_a, rt, hh * 128 + c * 32, v, fp16);
+                }
+                stage_done();
+            }
+            // ---------------------------------------------------------------- stage 1: MLP hidden
+            {
+                mbar_wait(acc_full, stage_it & 1);
+                tc_fence_after();
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t r[32];
+                    tmem_ld32(t_col + c * 32, r);
+                    tmem_ld_wait();
+                    const float* b = p.bias[1] + hh * 128 + c * 32;
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(b + j));
+                        v[j] = leaky_relu(__uint_as_float(r[j]) + b4.x); v[j + 1] = leaky_relu(__uint_as_float(r[j + 1]) + b4.y);
+                        v[j + 2] = leaky_relu(__uint_as_float(r[j + 2]) + b4.z); v[j + 3] = leaky_relu(__uint_as_float(r[j + 3]) + b4.w);
+                    }
+                    chain_store_a(s_a, rt, hh * 128 + c * 32, v, fp16);
+                }
+                stage_done();
+            }
+            // ---------------------------------------------------------------- stage 2: MLP output, residual, next layer's LN1 + modulate
+            {
+                const bool next = p.n_stages > 3;
+                float xr[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) xr[j] = 0.f;
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) ldg256(xrow + j, &xr[j]);            // x1, written by this thread in stage 0
+                }
+                mbar_wait(acc_full, stage_it & 1);
+                tc_fence_after();
+                float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t r[32];
+                    tmem_ld32(t_col + c * 32, r);
+                    tmem_ld_wait();
+                    chain_resid_chunk<true>(r, xr, p.bias[2] + hh * 128 + c * 32, p.gate_mlp + eo + c * 32, s1, s2);
+                    if (valid) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) stg256(xrow + c * 32 + j, &r[j]);
+                        if (c < 3) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8) ldg256(xrow + (c + 1) * 32 + j, &xr[j]);
+                        }
+                    }
+                    if (next) tmem_st32(t_col + c * 32, r);
+                }
+                if (next) {
+                    tmem_st_wait();
+                    st1[hh * 128 + rt] = make_float2(s1, s2);
+                    named_bar_sync(1, 256);
+                    const float2 o1 = st1[(hh ^ 1) * 128 + rt];
+                    const float mean = (s1 + o1.x) * inv_n;
+                    const float rstd = rsqrtf(fmaxf((s2 + o1.y) * inv_n - mean * mean, 0.f) + kLnEps);
+                    named_bar_sync(1, 256);
+#pragma unroll 1
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t r[32];
+                        tmem_ld32(t_col + c * 32, r);
+                        tmem_ld_wait();
+                        const float* lw = p.ln1_w + hh * 128 + c * 32; const float* lb = p.ln1_b + hh * 128 + c * 32;
+                        const float* sc = p.scale_nxt + eo + c * 32; const float* sh = p.shift_nxt + eo + c * 32;
+                        float v[32];
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 w4 = __ldg(reinterpret_cast<const float4*>(lw + j)), b4 = __ldg(reinterpret_cast<const float4*>(lb + j));
+                            const float4 s4 = *reinterpret_cast<const float4*>(sc + j), h4 = *reinterpret_cast<const float4*>(sh + j);
+                            const float ww[4] = {w4.x, w4.y, w4.z, w4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+                            const float ss[4] = {s4.x, s4.y, s4.z, s4.w}, hs[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const float y = fmaf((__uint_as_float(r[j + u]) - mean) * rstd, ww[u], bb[u]);
+                                v[j + u] = fmaf(y, 1.f + ss[u], hs[u]);
+                            }
+                        }
+                        chain_store_a(s_a, rt, hh * 128 + c * 32, v, fp16);
+                    }
+                }
+                stage_done();
+            }
+            // ---------------------------------------------------------------- stages 3-5: q, k, v of the next layer
+            if (p.n_stages > 3) {
+#pragma unroll 1
+                for (int g = 0; g < 3; ++g) {
+                    mbar_wait(acc_full, stage_it & 1);
+                    tc_fence_after();
+                    uint16_t* dst = reinterpret_cast<uint16_t*>(p.qkv) + (size_t)row * (3 * kChainH) + g * kChainH + hh * 128;
+#pragma unroll 1
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t r[32];
+                        tmem_ld32(t_col + c * 32, r);
+                        tmem_ld_wait();
+                        if (valid) {
+                            const float* b = p.bias[3 + g] + hh * 128 + c * 32;
+                            uint32_t pk[16];
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(b + j));
+                                pk[j >> 1] = pack16(__uint_as_float(r[j]) + b4.x, __uint_as_float(r[j + 1]) + b4.y, fp16);
+                                pk[(j >> 1) + 1] = pack16(__uint_as_float(r[j + 2]) + b4.z, __uint_as_float(r[j + 3]) + b4.w, fp16);
+                            }
+                            stg256(dst + c * 32, &pk[0]); stg256(dst + c * 32 + 16, &pk[8]);
+                        }
+                    }
+                    stage_done();
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
+}
+
+}  // namespace srhep

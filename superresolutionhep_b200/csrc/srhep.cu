@@ -18,6 +18,7 @@
 
 #include "kernels_f32.cuh"
 #include "kernels_bf16.cuh"
+#include "kernels_chain.cuh"
 
 using namespace srhep;
 
