@@ -104,6 +104,14 @@ int bf16_pack_weights(SrhepHandle* h, const float* wh) {
     memcpy(&b[bw.bias_head1], wh + L.h1.b, d.head_h1 * sizeof(float));
     CK(h, cudaMalloc(&bw.bias, b.size() * sizeof(float)));
     CK(h, cudaMemcpy(bw.bias, b.data(), b.size() * sizeof(float), cudaMemcpyHostToDevice));
+    bw.bias_h = (float*)malloc(b.size() * sizeof(float));
+    bw.bqkv_h = (float*)malloc((size_t)d.layers * 3 * H * sizeof(float));
+    if (!bw.bias_h || !bw.bqkv_h) return fail(h, SRHEP_E_NOMEM, "host allocation failed");
+    memcpy(bw.bias_h, b.data(), b.size() * sizeof(float));
+    for (int l = 0; l < d.layers; ++l) {
+        const Lin* qkv[3] = {&L.layers[l].q, &L.layers[l].k, &L.layers[l].v};
+        for (int j = 0; j < 3; ++j) memcpy(bw.bqkv_h + ((size_t)l * 3 + j) * H, wh + qkv[j]->b, H * sizeof(float));
+    }
     CK(h, cudaFuncSetAttribute(gemm_bf16_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_bf16_smem_bytes<256>(4)));
     CK(h, cudaFuncSetAttribute(gemm_bf16_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_bf16_smem_bytes<256>(4)));
     CK(h, cudaFuncSetAttribute(attn_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmemBytes));
@@ -117,6 +125,7 @@ void bf16_free_weights(SrhepHandle* h) {
     if (h->bw.img) cudaFree(h->bw.img);
     if (h->bw.bias) cudaFree(h->bw.bias);
     if (h->bw.tok_lp) cudaFree(h->bw.tok_lp);
+    free(h->bw.bias_h); free(h->bw.bqkv_h);
     h->bw = Bf16Weights();
 }
 
@@ -144,6 +153,7 @@ void launch_gemm_bf16(Engine& E, const CUtensorMap& tm, int M, int K, int N, con
     GemmBf16Params p;
     p.M = M; p.num_kb = K / 64; p.w_img = w_img; p.C = C; p.ldc = ldc; p.out_bf16 = out_bf16; p.ep = ep;
     p.fp16 = E.h->precision == SRHEP_PREC_FP16;
+    p.c_blocked = (kLN && !ep.resid && E.x_blocked && out_bf16 == 0) ? 1 : 0;
     const int m_tiles = (M + kGemmBM - 1) / kGemmBM, n_tiles = N / BN;
     dim3 grid(std::max(1, std::min(m_tiles, 148 / n_tiles)), n_tiles);
     static_assert(!kLN || BN == 256, "the fused LayerNorm epilogue maps 256 epilogue threads to 256 columns");
@@ -174,27 +184,43 @@ void launch_chain(Engine& E, int M, int l, const int* rev) {
     const int H = d.h_dim;
     const bool last = l + 1 == d.layers;
     const float* ml = h->mod + (size_t)l * 6 * H;
-    const float* bl = bw.bias + l * bw.bias_layer_stride;
     ChainParams q{};
     q.M = M; q.n_stages = last ? 3 : 6; q.fp16 = h->precision == SRHEP_PREC_FP16;
     q.row_event = rev; q.x = h->xres;
     q.w[0] = bw.img + bw.out[l]; q.w[1] = bw.img + bw.mlp1[l]; q.w[2] = bw.img + bw.mlp2[l];
-    q.bias[0] = bl; q.bias[1] = bl + H; q.bias[2] = bl + 2 * H;
+    const float* blh = bw.bias_h + l * bw.bias_layer_stride;
+    memcpy(q.cst[0], blh, 3 * H * sizeof(float));                      // out.b | mlp1.b | mlp2.b
+    memcpy(q.cst[6], blh + 5 * H, 2 * H * sizeof(float));              // norm2 w | b
     q.gate_msa = ml + 2 * H; q.shift_mlp = ml + 3 * H; q.scale_mlp = ml + 4 * H; q.gate_mlp = ml + 5 * H;
     q.ld_mod = h->mod_width;
-    q.ln2_w = bl + 5 * H; q.ln2_b = bl + 6 * H;
     if (!last) {
         const float* mn = h->mod + (size_t)(l + 1) * 6 * H;
-        const float* bn = bw.bias + (l + 1) * bw.bias_layer_stride;
-        for (int j = 0; j < 3; ++j) { q.w[3 + j] = bw.img + bw.qkv[l + 1] + (size_t)j * H * H * 2; q.bias[3 + j] = h->bqkv + ((size_t)(l + 1) * 3 + j) * H; }
+        for (int j = 0; j < 3; ++j) q.w[3 + j] = bw.img + bw.qkv[l + 1] + (size_t)j * H * H * 2;
+        memcpy(q.cst[3], bw.bqkv_h + (size_t)(l + 1) * 3 * H, 3 * H * sizeof(float));
+        memcpy(q.cst[8], bw.bias_h + (l + 1) * bw.bias_layer_stride + 3 * H, 2 * H * sizeof(float));     // next norm1 w | b
         q.shift_nxt = mn; q.scale_nxt = mn + H;
-        q.ln1_w = bn + 3 * H; q.ln1_b = bn + 4 * H;
         q.qkv = h->qkv_lp;
     }
     const int m_tiles = (M + 127) / 128;
     const int grid = std::max(1, std::min(m_tiles, 2 * 148));
+    static long long* dbg_dev = nullptr;
+    const bool dbg = getenv("SRHEP_CHAIN_DBG") && l == 1;
+    if (dbg) { if (!dbg_dev) cudaMalloc(&dbg_dev, 256 * sizeof(long long)); cudaMemsetAsync(dbg_dev, 0, 256 * sizeof(long long), E.s); q.dbg = dbg_dev; }
     layer_chain_kernel<<<grid, kChainThreads, kChainSmemBytes, E.s>>>(bw.tm_b, q);
     E.check("layer_chain");
+    if (dbg) {
+        long long hbuf[256];
+        cudaStreamSynchronize(E.s);
+        cudaMemcpy(hbuf, dbg_dev, sizeof hbuf, cudaMemcpyDeviceToHost);
+        static const char* names[26] = {"P a_free", "P A issued", "M tile start", "M a_full", "M g0", "M g1", "M g2", "M g3", "M g4", "M g5",
+                                        "E0 acc", "E0 done", "E1 acc", "E1 done", "E2 acc", "E2 done", "E3 acc", "E3 done", "E4 acc", "E4 done", "E5 acc", "E5 done", "E0 passA", "E0 bar1", "E0 passB", "E0 bar3"};
+        const long long t0 = hbuf[1];
+        for (int t = 0; t < 4; ++t) {
+            fprintf(stderr, "[chain dbg] tile %d (cycles since first A issue):", t);
+            for (int k = 0; k < 26; ++k) fprintf(stderr, " %s=%lld", names[k], hbuf[t * 32 + k] ? hbuf[t * 32 + k] - t0 : -1);
+            fprintf(stderr, "\n");
+        }
+    }
 }
 
 void bf16_forward(Engine& E, const Pass& p, const int* rev) {
@@ -204,6 +230,8 @@ void bf16_forward(Engine& E, const Pass& p, const int* rev) {
     const int fp16 = h->precision == SRHEP_PREC_FP16;
     float* x = h->xres;
     const float* mod = h->mod;
+    const bool chain = (H == kChainH && d.mlp_hid == kChainH) && !getenv("SRHEP_NO_CHAIN");
+    E.x_blocked = chain;
     __nv_bfloat16* a = (__nv_bfloat16*)h->act_a; __nv_bfloat16* b = (__nv_bfloat16*)h->act_b;
     __nv_bfloat16* qkv = (__nv_bfloat16*)h->qkv_lp;
     E.cat = SRHEP_CAT_FEAT0;
@@ -225,7 +253,6 @@ void bf16_forward(Engine& E, const Pass& p, const int* rev) {
       with_ln(ep, 0, false);
       launch_gemm_bf16<256, true>(E, bw.tm_tok, M, bw.feat0_kpad, H, bw.img + bw.feat0, x, H, 0, ep); }
     E.tap(h->tap_feat0, x, M);
-    const bool chain = (H == kChainH && d.mlp_hid == kChainH) && !getenv("SRHEP_NO_CHAIN");
     if (chain) {
         // layer 0's q|k|v come from the feat_0 GEMM's fused LN1; every later projection rides in the previous layer's chain kernel
         E.cat = SRHEP_CAT_QKV;

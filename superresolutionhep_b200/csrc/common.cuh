@@ -25,6 +25,14 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+// Blocked layout of the fp32 residual stream (h_dim = 256) used by the tcgen05 chain path: the epilogue threads
+// of a 128-row tile each own one row (TMEM lane = row), so a warp's 32-byte accesses would touch 32 different
+// 128-byte lines of a row-major matrix.  Here the 8 floats (32 B) of column group cg of the 128 rows of a tile
+// are contiguous: [tile][cg = col / 8 (32 groups)][row in tile (128)][8 floats] -> a warp access = 1 KB contiguous.
+__host__ __device__ __forceinline__ size_t xblk_index(int row, int col) {
+    return ((((size_t)(row >> 7) * 32 + (size_t)(col >> 3)) << 7) + (size_t)(row & 127)) * 8 + (size_t)(col & 7);
+}
+
 // One ODE stage = one network evaluation followed by `out = base + coef * v`.
 // Lives in device memory so that a captured CUDA graph of one evaluation can be replayed
 // for every stage: kernels read sp[*stage_idx].

@@ -140,6 +140,15 @@ __device__ __forceinline__ void stg256(void* p, const uint32_t* v) {
     asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                  ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
 }
+// streaming variants: do not allocate in L1 (keeps the small L1 for the per-event / per-column parameter rows)
+__device__ __forceinline__ void ldg256_stream(const float* p, float* d) {
+    asm volatile("ld.global.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3]), "=f"(d[4]), "=f"(d[5]), "=f"(d[6]), "=f"(d[7]) : "l"(p));
+}
+__device__ __forceinline__ void stg256_stream(void* p, const uint32_t* v) {
+    asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
 template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
@@ -175,6 +184,7 @@ struct GemmBf16Params {
     const uint8_t* w_img;   // [N / BN][num_kb][BN x 128 B] pre-swizzled bf16 weights
     void* C; int ldc; int out_bf16;   // out_bf16: C is 16-bit (operand format) instead of fp32
     int fp16;               // operand / 16-bit output format: 0 = bf16, 1 = fp16
+    int c_blocked;          // fp32 C in the blocked residual layout (common.cuh: xblk_index); LayerNorm-fused variant without residual only
     GemmEpilogue ep;
 };
 
@@ -351,9 +361,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
                                     v[c * 32 + j + u] = w; s1 += w; s2 = fmaf(w, w, s2);
                                 }
                             }
+                            if (p.c_blocked) {
+#pragma unroll
+                                for (int j = 0; j < 32; j += 8) stg256(reinterpret_cast<float*>(p.C) + xblk_index(row, colh + c * 32 + j), &vr[c * 32 + j]);
+                            } else {
                             float* dst = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + colh + c * 32;
 #pragma unroll
                             for (int j = 0; j < 32; j += 8) stg256(dst + j, &vr[c * 32 + j]);
+                            }
                         }
                     }
                 } else {
@@ -402,9 +417,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
                         }
 #pragma unroll
                         for (int j = 0; j < 32; ++j) { v[c * 32 + j] = w[j]; s1 += w[j]; s2 = fmaf(w[j], w[j], s2); }
+                        if (p.c_blocked) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8) stg256(reinterpret_cast<float*>(p.C) + xblk_index(row, col0 + j), &vr[c * 32 + j]);
+                        } else {
                         float* dst = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
 #pragma unroll
                         for (int j = 0; j < 32; j += 8) stg256(dst + j, &vr[c * 32 + j]);
+                        }
                     }
                 }
                 }
@@ -883,6 +903,8 @@ struct Bf16Weights {
     size_t feat0 = 0, head1 = 0;
     size_t qkv[64] = {0}, out[64] = {0}, mlp1[64] = {0}, mlp2[64] = {0};
     float* bias = nullptr;           // 16-byte aligned copies: per layer [out | mlp1 | mlp2], then head1
+    float* bias_h = nullptr;         // host mirror of `bias` (per-column constants travel by value into the chain kernel)
+    float* bqkv_h = nullptr;         // host mirror of the stacked q|k|v biases
     size_t bias_layer_stride = 0, bias_head1 = 0;
     __nv_bfloat16* tok_lp = nullptr; // [rows, feat0 K padded] bf16 copy of tok_feat (feat_0 GEMM A operand)
     int feat0_kpad = 0;

@@ -37,27 +37,25 @@ struct ChainParams {
     int n_stages;                // 6, or 3 for the last layer (no next attention)
     int fp16;                    // 16-bit operand format: 0 = bf16, 1 = fp16
     const int* row_event;        // [M] global event id of each row
-    float* x;                    // [M, 256] fp32 residual stream, updated in place
+    float* x;                    // fp32 residual stream in the BLOCKED layout (common.cuh: xblk_index), updated in place
     const uint8_t* w[6];         // pre-swizzled weight images [4 k-blocks][256 rows x 128 B]
-    const float* bias[6];        // [256] each
+    float cst[10][256];          // per-column constants BY VALUE (constant bank, no LSU traffic): biases of stages 0-5, norm2 w/b, next norm1 w/b
     const float* gate_msa;       // per-event rows (stride ld_mod floats)
     const float* shift_mlp; const float* scale_mlp; const float* gate_mlp;
     const float* shift_nxt; const float* scale_nxt;       // next layer's shift_msa / scale_msa
     int ld_mod;
-    const float* ln2_w; const float* ln2_b;                // this layer's norm2 affine
-    const float* ln1_w; const float* ln1_b;                // next layer's norm1 affine
     void* qkv;                   // [M, 768] 16-bit q|k|v of the next layer
+    long long* dbg;              // optional timeline of CTA 0 (clock64 stamps, 32 per tile, first 8 tiles); null in production
 };
 
 // acc + bias (+ LeakyReLU), gated into the residual: returns the new residual chunk in r[] (as bits)
 template <bool kAct>
-__device__ __forceinline__ void chain_resid_chunk(uint32_t (&r)[32], const float (&xr)[32], const float* __restrict__ bias,
+__device__ __forceinline__ void chain_resid_chunk(uint32_t (&r)[32], const float (&xr)[32], const float* bias /*constant bank*/,
                                                   const float* __restrict__ gate, float& s1, float& s2) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + j));
         const float4 g4 = *reinterpret_cast<const float4*>(gate + j);
-        const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w};
+        const float bb[4] = {bias[j], bias[j + 1], bias[j + 2], bias[j + 3]}, gg[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             float w = __uint_as_float(r[j + u]) + bb[u];
@@ -80,7 +78,9 @@ __device__ __forceinline__ void chain_store_a(uint8_t* s_a, int rt, int col0, co
                        pack16(v[8 * g + 4], v[8 * g + 5], fp16), pack16(v[8 * g + 6], v[8 * g + 7], fp16));
 }
 
-__global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __grid_constant__ CUtensorMap tmap_a, ChainParams p) {
+#define CHAIN_STAMP(tile, k) do { if (p.dbg && blockIdx.x == 0 && (tile) < 8) p.dbg[(tile) * 32 + (k)] = clock64(); } while (0)
+
+__global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ ChainParams p) {
     extern __shared__ __align__(1024) uint8_t chain_smem[];      // no static smem in this kernel: the dynamic window starts 1024-aligned
     uint8_t* s_a = chain_smem;
     if ((smem_u32(s_a) & 1023u) != 0) __trap();
@@ -119,9 +119,11 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                 for (int j = 0; j < slots_per_tile; ++j, ++slot_it) {
                     if (j == (tile_i == 0 ? 0 : 2)) {                 // the A tile: first thing of the kernel, else after two weight slots of run-ahead
                         if (tile_i > 0) mbar_wait(a_free, (tile_i - 1) & 1);
+                        CHAIN_STAMP(tile_i, 0);
                         mbar_expect_tx(a_full, kChainABytes);
 #pragma unroll
                         for (int kb = 0; kb < 4; ++kb) tma_load_2d(s_a + kb * 16384, &tmap_a, a_full, kb * 64, t * 128);
+                        CHAIN_STAMP(tile_i, 1);
                     }
                     const int g = j >> 3, kb = (j >> 1) & 3, nh = j & 1;
                     const uint32_t s = slot_it % kChainSlots, ph = (slot_it / kChainSlots) & 1;
@@ -137,7 +139,7 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
         for (int t = blockIdx.x; t < m_tiles; t += gridDim.x, ++tile_i) {
             for (int g = 0; g < p.n_stages; ++g, ++stage_it) {
                 if (stage_it > 0) mbar_wait(epi_done, (stage_it - 1) & 1);      // accumulator drained, A operand of this stage in place
-                if (g == 0) mbar_wait(a_full, tile_i & 1);
+                if (g == 0) { if (lane == 0) CHAIN_STAMP(tile_i, 2); mbar_wait(a_full, tile_i & 1); if (lane == 0) CHAIN_STAMP(tile_i, 3); }
                 tc_fence_after();
                 for (int j = 0; j < 8; ++j, ++slot_it) {
                     const int kb = j >> 1, nh = j & 1;
@@ -158,6 +160,7 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                     }
                     __syncwarp();
                 }
+                if (lane == 0) CHAIN_STAMP(tile_i, 4 + g);
             }
         }
     } else {
@@ -167,19 +170,20 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
         float2* st1 = reinterpret_cast<float2*>(s_a);                  // LayerNorm partial sums: scratch inside the (then dead) A buffer
         float2* st2 = st1 + 256;
         const int fp16 = p.fp16;
-        uint32_t stage_it = 0;
+        uint32_t stage_it = 0, tile_i = 0;
         auto stage_done = [&]() {
+            if (warp == 2 && lane == 0) CHAIN_STAMP(tile_i, 11 + 2 * (int)(stage_it % (uint32_t)p.n_stages));
             fence_async_smem();                                        // A stores -> visible to the tensor-core (async) proxy
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(epi_done);
             ++stage_it;
         };
-        for (int t = blockIdx.x; t < m_tiles; t += gridDim.x) {
+        for (int t = blockIdx.x; t < m_tiles; t += gridDim.x, ++tile_i) {
             const int row = t * 128 + rt;
             const bool valid = row < p.M;
             const int evt = valid ? p.row_event[row] : 0;
-            float* xrow = p.x + (size_t)row * kChainH + hh * 128;
+            float* xrow = p.x + xblk_index(row, hh * 128);         // + 1024 floats per 8-column group (32 B pieces of this row)
             const size_t eo = (size_t)evt * p.ld_mod + hh * 128;
             constexpr float inv_n = 1.0f / (float)kChainH;
 
@@ -190,9 +194,10 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                 for (int j = 0; j < 32; ++j) xr[j] = 0.f;
                 if (valid) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 8) ldg256(xrow + j, &xr[j]);            // in flight while the MMAs run
+                    for (int j = 0; j < 32; j += 8) ldg256_stream(xrow + (j >> 3) * 1024, &xr[j]);   // in flight while the MMAs run
                 }
                 mbar_wait(acc_full, stage_it & 1);
+                if (warp == 2 && lane == 0) CHAIN_STAMP(tile_i, 10);
                 tc_fence_after();
                 float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
@@ -200,20 +205,22 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                     uint32_t r[32];
                     tmem_ld32(t_col + c * 32, r);
                     tmem_ld_wait();
-                    chain_resid_chunk<false>(r, xr, p.bias[0] + hh * 128 + c * 32, p.gate_msa + eo + c * 32, s1, s2);
+                    chain_resid_chunk<false>(r, xr, &p.cst[0][hh * 128 + c * 32], p.gate_msa + eo + c * 32, s1, s2);
                     if (valid) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 8) stg256(xrow + c * 32 + j, &r[j]);
+                        for (int j = 0; j < 32; j += 8) stg256_stream(xrow + (c * 4 + (j >> 3)) * 1024, &r[j]);
                         if (c < 3) {
 #pragma unroll
-                            for (int j = 0; j < 32; j += 8) ldg256(xrow + (c + 1) * 32 + j, &xr[j]);
+                            for (int j = 0; j < 32; j += 8) ldg256_stream(xrow + ((c + 1) * 4 + (j >> 3)) * 1024, &xr[j]);
                         }
                     }
                     tmem_st32(t_col + c * 32, r);
                 }
+                if (warp == 2 && lane == 0) CHAIN_STAMP(tile_i, 22);
                 tmem_st_wait();
                 st1[hh * 128 + rt] = make_float2(s1, s2);
                 named_bar_sync(1, 256);
+                if (warp == 2 && lane == 0) CHAIN_STAMP(tile_i, 23);
                 const float2 o1 = st1[(hh ^ 1) * 128 + rt];
                 float mean = (s1 + o1.x) * inv_n;
                 float rstd = rsqrtf(fmaxf((s2 + o1.y) * inv_n - mean * mean, 0.f) + kLnEps);
@@ -223,13 +230,12 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                     uint32_t r[32];
                     tmem_ld32(t_col + c * 32, r);
                     tmem_ld_wait();
-                    const float* lw = p.ln2_w + hh * 128 + c * 32; const float* lb = p.ln2_b + hh * 128 + c * 32;
+                    const float* lw = &p.cst[6][hh * 128 + c * 32]; const float* lb = &p.cst[7][hh * 128 + c * 32];
                     const float* sc = p.scale_mlp + eo + c * 32; const float* sh = p.shift_mlp + eo + c * 32;
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
-                        const float4 w4 = __ldg(reinterpret_cast<const float4*>(lw + j)), b4 = __ldg(reinterpret_cast<const float4*>(lb + j));
                         const float4 s4 = *reinterpret_cast<const float4*>(sc + j), h4 = *reinterpret_cast<const float4*>(sh + j);
-                        const float ww[4] = {w4.x, w4.y, w4.z, w4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+                        const float ww[4] = {lw[j], lw[j + 1], lw[j + 2], lw[j + 3]}, bb[4] = {lb[j], lb[j + 1], lb[j + 2], lb[j + 3]};
                         const float ss[4] = {s4.x, s4.y, s4.z, s4.w}, hs[4] = {h4.x, h4.y, h4.z, h4.w};
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
@@ -241,6 +247,7 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                     }
                     tmem_st32(t_col + c * 32, r);
                 }
+                if (warp == 2 && lane == 0) CHAIN_STAMP(tile_i, 24);
                 tmem_st_wait();
                 st2[hh * 128 + rt] = make_float2(t1, t2);
                 named_bar_sync(1, 256);
@@ -248,6 +255,7 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                 mean = (t1 + o2.x) * inv_n;
                 rstd = rsqrtf(fmaxf((t2 + o2.y) * inv_n - mean * mean, 0.f) + kLnEps);
                 named_bar_sync(1, 256);                                  // every thread has read its partner's sums: the scratch may be overwritten
+                if (warp == 2 && lane == 0) CHAIN_STAMP(tile_i, 25);
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {                            // the Dense's own non-affine LayerNorm (models/dense.py:62) -> A
                     uint32_t r[32];
@@ -263,20 +271,17 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
             // ---------------------------------------------------------------- stage 1: MLP hidden
             {
                 mbar_wait(acc_full, stage_it & 1);
+                if (warp == 2 && lane == 0) CHAIN_STAMP(tile_i, 12);
                 tc_fence_after();
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
                     uint32_t r[32];
                     tmem_ld32(t_col + c * 32, r);
                     tmem_ld_wait();
-                    const float* b = p.bias[1] + hh * 128 + c * 32;
+                    const float* b = &p.cst[1][hh * 128 + c * 32];
                     float v[32];
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(b + j));
-                        v[j] = leaky_relu(__uint_as_float(r[j]) + b4.x); v[j + 1] = leaky_relu(__uint_as_float(r[j + 1]) + b4.y);
-                        v[j + 2] = leaky_relu(__uint_as_float(r[j + 2]) + b4.z); v[j + 3] = leaky_relu(__uint_as_float(r[j + 3]) + b4.w);
-                    }
+                    for (int j = 0; j < 32; ++j) v[j] = leaky_relu(__uint_as_float(r[j]) + b[j]);
                     chain_store_a(s_a, rt, hh * 128 + c * 32, v, fp16);
                 }
                 stage_done();
@@ -289,9 +294,10 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                 for (int j = 0; j < 32; ++j) xr[j] = 0.f;
                 if (valid) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 8) ldg256(xrow + j, &xr[j]);            // x1, written by this thread in stage 0
+                    for (int j = 0; j < 32; j += 8) ldg256_stream(xrow + (j >> 3) * 1024, &xr[j]);   // x1, written by this thread in stage 0
                 }
                 mbar_wait(acc_full, stage_it & 1);
+                if (warp == 2 && lane == 0) CHAIN_STAMP(tile_i, 14);
                 tc_fence_after();
                 float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
@@ -299,13 +305,13 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                     uint32_t r[32];
                     tmem_ld32(t_col + c * 32, r);
                     tmem_ld_wait();
-                    chain_resid_chunk<true>(r, xr, p.bias[2] + hh * 128 + c * 32, p.gate_mlp + eo + c * 32, s1, s2);
+                    chain_resid_chunk<true>(r, xr, &p.cst[2][hh * 128 + c * 32], p.gate_mlp + eo + c * 32, s1, s2);
                     if (valid) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 8) stg256(xrow + c * 32 + j, &r[j]);
+                        for (int j = 0; j < 32; j += 8) stg256_stream(xrow + (c * 4 + (j >> 3)) * 1024, &r[j]);
                         if (c < 3) {
 #pragma unroll
-                            for (int j = 0; j < 32; j += 8) ldg256(xrow + (c + 1) * 32 + j, &xr[j]);
+                            for (int j = 0; j < 32; j += 8) ldg256_stream(xrow + ((c + 1) * 4 + (j >> 3)) * 1024, &xr[j]);
                         }
                     }
                     if (next) tmem_st32(t_col + c * 32, r);
@@ -323,14 +329,13 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                         uint32_t r[32];
                         tmem_ld32(t_col + c * 32, r);
                         tmem_ld_wait();
-                        const float* lw = p.ln1_w + hh * 128 + c * 32; const float* lb = p.ln1_b + hh * 128 + c * 32;
+                        const float* lw = &p.cst[8][hh * 128 + c * 32]; const float* lb = &p.cst[9][hh * 128 + c * 32];
                         const float* sc = p.scale_nxt + eo + c * 32; const float* sh = p.shift_nxt + eo + c * 32;
                         float v[32];
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
-                            const float4 w4 = __ldg(reinterpret_cast<const float4*>(lw + j)), b4 = __ldg(reinterpret_cast<const float4*>(lb + j));
                             const float4 s4 = *reinterpret_cast<const float4*>(sc + j), h4 = *reinterpret_cast<const float4*>(sh + j);
-                            const float ww[4] = {w4.x, w4.y, w4.z, w4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+                            const float ww[4] = {lw[j], lw[j + 1], lw[j + 2], lw[j + 3]}, bb[4] = {lb[j], lb[j + 1], lb[j + 2], lb[j + 3]};
                             const float ss[4] = {s4.x, s4.y, s4.z, s4.w}, hs[4] = {h4.x, h4.y, h4.z, h4.w};
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
@@ -348,6 +353,7 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
 #pragma unroll 1
                 for (int g = 0; g < 3; ++g) {
                     mbar_wait(acc_full, stage_it & 1);
+                    if (warp == 2 && lane == 0) CHAIN_STAMP(tile_i, 16 + 2 * g);
                     tc_fence_after();
                     uint16_t* dst = reinterpret_cast<uint16_t*>(p.qkv) + (size_t)row * (3 * kChainH) + g * kChainH + hh * 128;
 #pragma unroll 1
@@ -356,14 +362,10 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                         tmem_ld32(t_col + c * 32, r);
                         tmem_ld_wait();
                         if (valid) {
-                            const float* b = p.bias[3 + g] + hh * 128 + c * 32;
+                            const float* b = &p.cst[3 + g][hh * 128 + c * 32];
                             uint32_t pk[16];
 #pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(b + j));
-                                pk[j >> 1] = pack16(__uint_as_float(r[j]) + b4.x, __uint_as_float(r[j + 1]) + b4.y, fp16);
-                                pk[(j >> 1) + 1] = pack16(__uint_as_float(r[j + 2]) + b4.z, __uint_as_float(r[j + 3]) + b4.w, fp16);
-                            }
+                            for (int j = 0; j < 32; j += 2) pk[j >> 1] = pack16(__uint_as_float(r[j]) + b[j], __uint_as_float(r[j + 1]) + b[j + 1], fp16);
                             stg256(dst + c * 32, &pk[0]); stg256(dst + c * 32 + 16, &pk[8]);
                         }
                     }

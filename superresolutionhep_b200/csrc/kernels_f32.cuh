@@ -534,6 +534,7 @@ struct HeadPrepParams {
     const int* row_event;
     int M, h, cond;
     float* final_tap;                     // optional [Tp, h]: final_norm(x)
+    int x_blocked;                        // x in the blocked residual layout (common.cuh: xblk_index)
 };
 
 template <typename OutT, int PH, int PC, int PX>     // per-lane counts: h/32, cond/32, ctx/32
@@ -546,7 +547,7 @@ __global__ void __launch_bounds__(256) head_prep_kernel(HeadPrepParams p, OutT* 
     float v[PT];                         // [0,PH) final_norm part, [PH,PV) cond_feat, [PV,PT) context
     float s = 0.f, q = 0.f;
 #pragma unroll
-    for (int j = 0; j < PH; ++j) { v[j] = p.x[(size_t)row * p.ldx + lane + 32 * j]; s += v[j]; }
+    for (int j = 0; j < PH; ++j) { v[j] = p.x_blocked ? p.x[xblk_index(row, lane + 32 * j)] : p.x[(size_t)row * p.ldx + lane + 32 * j]; s += v[j]; }
     s = warp_sum(s);
     float mean = s / (float)p.h;
 #pragma unroll
@@ -606,6 +607,13 @@ __global__ void __launch_bounds__(256) head_prep_kernel(HeadPrepParams p, OutT* 
 //    euler / midpoint stage update of torchdiffeq's fixed-grid solvers).
 //    One warp per row; weights transposed in shared memory (bank-conflict free).
 // ------------------------------------------------------------------------------------
+// blocked residual layout -> row-major [M, 256] (debug taps only)
+__global__ void unblock_x_kernel(const float* __restrict__ xb, float* __restrict__ out, int M) {
+    const size_t n = (size_t)M * 256;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = xb[xblk_index((int)(i >> 8), (int)(i & 255))];
+}
+
 struct HeadTailParams {
     const float* h1; int ldh; int M;
     const float* w2; const float* b2;     // [H2, H1]

@@ -228,6 +228,7 @@ struct Engine {
     int rc = 0;
     Profiler* prof = nullptr;
     int cat = 0;
+    bool x_blocked = false;          // residual stream of the current evaluation is in the blocked layout (tcgen05 chain path)
 
     const float* W(size_t off) const { return h->w + off; }
 
@@ -416,11 +417,17 @@ struct Engine {
         q.ctx = h->ctx; q.ctx_dim = d.ctx; q.row_event = h->row_event + p.r0;
         q.M = p.r1 - p.r0; q.h = d.h_dim; q.cond = d.cond;
         q.final_tap = h->debug ? h->tap_final : nullptr;
+        q.x_blocked = x_blocked ? 1 : 0;
         return q;
     }
 
     void tap(float* dst, const float* src, int M) {
         if (rc || !h->debug || !dst) return;
+        if (x_blocked) {
+            unblock_x_kernel<<<std::min((M * 256 + 255) / 256, 148 * 8), 256, 0, s>>>(src, dst, M);
+            check("unblock_x");
+            return;
+        }
         cudaError_t e = cudaMemcpyAsync(dst, src, (size_t)M * h->d.h_dim * sizeof(float), cudaMemcpyDeviceToDevice, s);
         if (e != cudaSuccess) rc = fail(h, SRHEP_E_CUDA, "tap copy: %s", cudaGetErrorString(e));
     }
