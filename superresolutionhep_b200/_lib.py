@@ -24,6 +24,26 @@ EXPORTS = (
 )
 
 
+PFLOW_EXPORTS = ("pflow_weight_count", "pflow_create", "pflow_destroy", "pflow_last_error", "pflow_forward", "pflow_launch_count")
+
+
+class PflowDimsC(C.Structure):
+    """Mirror of ``PflowDims`` in include/pflow.h."""
+    _fields_ = [("h_dim", C.c_int32), ("heads", C.c_int32), ("enc_layers", C.c_int32), ("kin_layers", C.c_int32),
+                ("layer_emb_dim", C.c_int32), ("max_particles", C.c_int32), ("part_emb_dim", C.c_int32),
+                ("card_n_hidden", C.c_int32), ("card_hidden", C.c_int32 * 4), ("card_out", C.c_int32)]
+
+
+class PflowVarTransformC(C.Structure):
+    """Mirror of ``PflowVarTransform`` in include/pflow.h."""
+    _fields_ = [("trans", C.c_int32), ("m", C.c_float), ("scale", C.c_int32), ("mean", C.c_float), ("std", C.c_float),
+                ("min", C.c_float), ("max", C.c_float), ("lo", C.c_float), ("hi", C.c_float)]
+
+
+class PflowCells(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("e", "eta", "cosphi", "sinphi", "phi", "e_raw", "eta_raw", "layer")]
+
+
 class SrhepCond(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("eta", "cosphi", "sinphi", "e_proxy", "layer")]
 
@@ -69,8 +89,26 @@ def load() -> C.CDLL:
     lib.srhep_profile.argtypes = [vp, vp, f32, vp, C.POINTER(f32), C.POINTER(i32), vp]
     lib.srhep_launch_count.restype = u64
     lib.srhep_launch_count.argtypes = [vp]
+    lib.pflow_weight_count.restype = C.c_size_t
+    lib.pflow_weight_count.argtypes = [C.POINTER(PflowDimsC)]
+    lib.pflow_create.restype = C.c_int
+    lib.pflow_create.argtypes = [C.c_int, C.POINTER(PflowDimsC), vp, C.c_size_t, C.POINTER(PflowVarTransformC), C.POINTER(vp)]
+    lib.pflow_destroy.restype = C.c_int
+    lib.pflow_destroy.argtypes = [vp]
+    lib.pflow_last_error.restype = C.c_char_p
+    lib.pflow_last_error.argtypes = [vp]
+    lib.pflow_forward.restype = C.c_int
+    lib.pflow_forward.argtypes = [vp, C.POINTER(PflowCells), vp, i32, vp, vp, vp, vp, vp, vp]
+    lib.pflow_launch_count.restype = u64
+    lib.pflow_launch_count.argtypes = [vp]
     _LIB = lib
     return lib
+
+
+def check_pflow(lib: C.CDLL, handle, rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib.pflow_last_error(handle)
+        raise RuntimeError(f"{what} failed (code {rc}): {msg.decode() if msg else '?'}")
 
 
 def check(lib: C.CDLL, handle, rc: int, what: str) -> None:

@@ -1109,3 +1109,5 @@ int srhep_get_tap(SrhepHandle* h, const char* name, float* out, size_t n_floats,
 }
 
 }  // extern "C"
+
+#include "pflow.inl"

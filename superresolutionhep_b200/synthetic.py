@@ -93,3 +93,37 @@ def synthetic_noise(batch: Dict[str, torch.Tensor], seed: int = 0) -> torch.Tens
     reference's ``randn_like(e_proxy)`` does, flow_model.py:319) so CPU and GPU runs share it."""
     g = torch.Generator().manual_seed(seed)
     return torch.randn(batch["e_proxy"].shape, generator=g)
+
+
+def synthetic_pflow_events(n_events: int, seed: int = 4321, counts: Optional[np.ndarray] = None,
+                           pad_to: Optional[int] = None) -> Dict[str, torch.Tensor]:
+    """Padded batch dict with the keys ``SAPF.forward`` reads (pflow/dataset_pf.py:246-259):
+    cells of the SR output above 1 MeV: ``e_raw ~ 1 + Exp(50)`` MeV,
+    ``cell_e = (sqrt(e_raw) - 7.35) / 15.65``, ``cell_eta = eta_raw / 2.988``."""
+    rng = np.random.default_rng(seed)
+    n = cell_counts("pflow", n_events, rng) if counts is None else np.asarray(counts, dtype=np.int64)
+    n_events = len(n)
+    nmax = int(max(int(n.max()) if n_events else 1, 1))
+    if pad_to is not None:
+        nmax = max(nmax, pad_to)
+    z = lambda: np.zeros((n_events, nmax), np.float32)
+    e, eta, phi, cosphi, sinphi, e_raw, eta_raw = z(), z(), z(), z(), z(), z(), z()
+    layer = np.zeros((n_events, nmax), np.int32)
+    mask = np.zeros((n_events, nmax), bool)
+    for i, ni in enumerate(n):
+        ni = int(ni)
+        n_blob = int(rng.integers(1, 5))                                   # 1-4 particles' worth of energy blobs
+        c_eta, c_phi = rng.uniform(-2.3, 2.3, n_blob), rng.uniform(-np.pi, np.pi, n_blob)
+        which = rng.integers(0, n_blob, ni)
+        er = (1.0 + rng.exponential(50.0, ni)).astype(np.float32)
+        etar = (c_eta[which] + rng.normal(0, 0.08, ni)).astype(np.float32)
+        ph = (c_phi[which] + rng.normal(0, 0.08, ni)).astype(np.float32)
+        e_raw[i, :ni] = er; eta_raw[i, :ni] = etar; phi[i, :ni] = ph
+        e[i, :ni] = (np.sqrt(er) - 7.35) / 15.65
+        eta[i, :ni] = etar / 2.988
+        cosphi[i, :ni] = np.cos(ph); sinphi[i, :ni] = np.sin(ph)
+        layer[i, :ni] = rng.integers(0, 3, ni)
+        mask[i, :ni] = True
+    t = torch.from_numpy
+    return {"cell_e": t(e), "cell_eta": t(eta), "cell_phi": t(phi), "cell_cosphi": t(cosphi), "cell_sinphi": t(sinphi),
+            "cell_layer": t(layer), "cell_mask": t(mask), "cell_e_raw": t(e_raw), "cell_eta_raw": t(eta_raw)}

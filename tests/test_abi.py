@@ -22,10 +22,10 @@ def lib():
     return _lib.load()
 
 
-def _declared_functions():
-    src = open(os.path.join(ROOT, "include", "srhep.h")).read()
+def _declared_functions(header="srhep.h", prefix="srhep_"):
+    src = open(os.path.join(ROOT, "include", header)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(srhep_\w+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(" + prefix + r"\w+)\s*\(", src)))
 
 
 def test_every_declared_symbol_is_exported(lib):
@@ -35,6 +35,33 @@ def test_every_declared_symbol_is_exported(lib):
         assert hasattr(lib, n), f"{n} declared in include/srhep.h but not exported"
     assert set(names) == set(_lib.EXPORTS)
     assert b"sm_100a" in lib.srhep_version()
+
+
+def test_every_declared_pflow_symbol_is_exported(lib):
+    names = _declared_functions("pflow.h", "pflow_")
+    assert len(names) == 6
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/pflow.h but not exported"
+    assert set(names) == set(_lib.PFLOW_EXPORTS)
+
+
+def test_pflow_weight_layout_matches_reference_checkpoint(lib, golden_dir):
+    """The drop-in SAPF has the reference's state_dict keys, order and shapes (real pf_hr checkpoint)."""
+    from superresolutionhep_b200.default_configs import pflow_config, pflow_var_transform
+    from superresolutionhep_b200.pflow import PflowLightning, SAPF
+    g = torch.load(os.path.join(golden_dir, "pflow_pf_hr.pt"))
+    m = SAPF(pflow_config(), inference=True)
+    assert list(m.state_dict().keys()) == list(g["state_dict"].keys())
+    assert m.load_state_dict(g["state_dict"], strict=True).missing_keys == []
+    assert lib.pflow_weight_count(C.byref(m.dims)) == 333537
+    lm = PflowLightning({"pf_model": g["pf_model"], "var_transform": g["var_transform"]}, {}, inference=True)
+    lm.load_state_dict({"net." + k: v for k, v in g["state_dict"].items()}, strict=True)        # Lightning checkpoint keys
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        from superresolutionhep_b200.synthetic import synthetic_pflow_events
+        lm.net(synthetic_pflow_events(1, counts=[16]))
+    bad = pflow_config(); bad["kinematics_predictor"]["use_attn_kinematics"] = False
+    with pytest.raises(ValueError):
+        SAPF(bad)
 
 
 @pytest.mark.parametrize("kind", ["single_e", "multipart"])
