@@ -73,6 +73,8 @@ int bf16_pack_weights(SrhepHandle* h, const float* wh) {
     for (int l = 0; l < d.layers; ++l) { bw.qkv[l] = take(3 * H, H); bw.out[l] = take(H, H); bw.mlp1[l] = take(H, H); bw.mlp2[l] = take(H, H); }
     const int hk = d.v_in + d.ctx;
     bw.head1 = take(d.head_h1, hk);
+    bw.head_chain = hk == kHeadK1 && d.head_h1 == kHeadH1 && d.head_h2 == kHeadH2 && d.head_h3 == kHeadH3;
+    if (bw.head_chain) { bw.head2 = take(kHeadH2, kHeadH1); bw.head3 = take(kHeadH3, kHeadH2); }
     std::vector<uint8_t> img(off);
     const bool fp16 = h->precision == SRHEP_PREC_FP16;
     pack_weight(img, bw.feat0, wh + L.feat0.w, L.feat0.in, H, ncol, bw.feat0_kpad, 256, fp16);
@@ -85,6 +87,13 @@ int bf16_pack_weights(SrhepHandle* h, const float* wh) {
         pack_weight(img, bw.mlp2[l], wh + y.m2.w, H, H, H, H, 256, fp16);
     }
     pack_weight(img, bw.head1, wh + L.h1.w, hk, d.head_h1, hk, hk, 128, fp16);
+    if (bw.head_chain) {
+        pack_weight(img, bw.head2, wh + L.h2.w, kHeadH1, kHeadH2, kHeadH1, kHeadH1, kHeadH2, fp16);
+        pack_weight(img, bw.head3, wh + L.h3.w, kHeadH2, kHeadH3, kHeadH2, kHeadH2, kHeadH3, fp16);
+        memcpy(bw.head_b1, wh + L.h1.b, sizeof bw.head_b1); memcpy(bw.head_b2, wh + L.h2.b, sizeof bw.head_b2);
+        memcpy(bw.head_b3, wh + L.h3.b, sizeof bw.head_b3); memcpy(bw.head_w4, wh + L.h4.w, sizeof bw.head_w4);
+        bw.head_b4 = wh[L.h4.b];
+    }
     CK(h, cudaMalloc(&bw.img, img.size()));
     CK(h, cudaMemcpy(bw.img, img.data(), img.size(), cudaMemcpyHostToDevice));
     bw.bytes = img.size();
@@ -115,6 +124,7 @@ int bf16_pack_weights(SrhepHandle* h, const float* wh) {
     CK(h, cudaFuncSetAttribute(gemm_bf16_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_bf16_smem_bytes<256>(4)));
     CK(h, cudaFuncSetAttribute(gemm_bf16_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_bf16_smem_bytes<256>(4)));
     CK(h, cudaFuncSetAttribute(attn_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmemBytes));
+    CK(h, cudaFuncSetAttribute(head_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeadSmemBytes));
     CK(h, cudaFuncSetAttribute(layer_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemBytes));
     CK(h, cudaFuncSetAttribute(layer_chain_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CK(h, cudaFuncSetAttribute(gemm_bf16_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_bf16_smem_bytes<128>(hk / 64)));
@@ -223,7 +233,7 @@ void launch_chain(Engine& E, int M, int l, const int* rev) {
     }
 }
 
-void bf16_forward(Engine& E, const Pass& p, const int* rev) {
+void bf16_forward(Engine& E, const Pass& p, const int* rev, const StageRef& st) {
     SrhepHandle* h = E.h;
     const SrhepDims& d = h->d; const Layout& L = h->L; Bf16Weights& bw = h->bw;
     const int M = p.r1 - p.r0, H = d.h_dim, ncol = d.cond + d.noisy_out;
@@ -304,6 +314,21 @@ void bf16_forward(Engine& E, const Pass& p, const int* rev) {
     } else {
     if (fp16) E.head_prep<__half>(E.head_params(p, x), (__half*)a, hw);
     else E.head_prep<__nv_bfloat16>(E.head_params(p, x), a, hw);
+    E.head_done = false;
+    if (bw.head_chain && !getenv("SRHEP_NO_HEADCHAIN")) {
+        if (!E.rc) {
+            HeadChainParams q;
+            q.M = M; q.fp16 = fp16; q.final_ln = d.head_final_ln;
+            q.w1 = bw.img + bw.head1; q.w2 = bw.img + bw.head2; q.w3 = bw.img + bw.head3;
+            memcpy(q.b1, bw.head_b1, sizeof q.b1); memcpy(q.b2, bw.head_b2, sizeof q.b2); memcpy(q.b3, bw.head_b3, sizeof q.b3);
+            memcpy(q.w4, bw.head_w4, sizeof q.w4); q.b4 = bw.head_b4;
+            q.stage = st;
+            const int m_tiles = (M + 127) / 128;
+            head_chain_kernel<<<std::max(1, std::min(m_tiles, 148)), kHeadThreads, kHeadSmemBytes, E.s>>>(bw.tm_hin, q);
+            E.check("head_chain");
+            E.head_done = true;
+        }
+    } else
     { GemmEpilogue ep; ep.bias = bw.bias + bw.bias_head1; ep.act = 1;
       launch_gemm_bf16<128>(E, bw.tm_hin, M, hw, d.head_h1, bw.img + bw.head1, h->h1buf, d.head_h1, 0, ep); }
     }

@@ -900,7 +900,9 @@ struct Bf16Weights {
     uint8_t* img = nullptr;          // all pre-swizzled weight images, one allocation
     size_t bytes = 0;
     // offsets (bytes) into img
-    size_t feat0 = 0, head1 = 0;
+    size_t feat0 = 0, head1 = 0, head2 = 0, head3 = 0;
+    bool head_chain = false;         // fused tcgen05 head available (kernels_head.cuh)
+    float head_b1[128], head_b2[64], head_b3[32], head_w4[32], head_b4;
     size_t qkv[64] = {0}, out[64] = {0}, mlp1[64] = {0}, mlp2[64] = {0};
     float* bias = nullptr;           // 16-byte aligned copies: per layer [out | mlp1 | mlp2], then head1
     float* bias_h = nullptr;         // host mirror of `bias` (per-column constants travel by value into the chain kernel)

@@ -19,6 +19,7 @@
 #include "kernels_f32.cuh"
 #include "kernels_bf16.cuh"
 #include "kernels_chain.cuh"
+#include "kernels_head.cuh"
 
 using namespace srhep;
 
@@ -211,7 +212,7 @@ int validate_dims(const SrhepDims& d) {
 // launch helpers
 // ----------------------------------------------------------------------------------------
 struct Engine;
-void bf16_forward(Engine& E, const Pass& p, const int* rev);      // bf16_forward.inl
+void bf16_forward(Engine& E, const Pass& p, const int* rev, const StageRef& st);      // bf16_forward.inl
 int bf16_pack_weights(SrhepHandle* h, const float* weights_host);
 void bf16_free_weights(SrhepHandle* h);
 int bf16_on_bind(SrhepHandle* h);
@@ -228,6 +229,7 @@ struct Engine {
     int rc = 0;
     Profiler* prof = nullptr;
     int cat = 0;
+    bool head_done = false;          // the tcgen05 head chain already produced v and the ODE update for this evaluation
     bool x_blocked = false;          // residual stream of the current evaluation is in the blocked layout (tcgen05 chain path)
 
     const float* W(size_t off) const { return h->w + off; }
@@ -392,10 +394,10 @@ struct Engine {
             { GemmEpilogue ep; ep.bias = W(L.h1.b); ep.act = 1;
               gemm_f32<float>(a, hw, W(L.h1.w), hw, h->h1buf, d.head_h1, M, d.head_h1, hw, ep); }
         } else {
-            bf16_forward(*this, p, rev);
+            bf16_forward(*this, p, rev, st);
         }
         cat = SRHEP_CAT_HEAD;
-        {   // head tail + ODE update
+        if (!head_done) {   // head tail + ODE update
             HeadTailParams q;
             q.h1 = h->h1buf; q.ldh = d.head_h1; q.M = M;
             q.w2 = W(L.h2.w); q.b2 = W(L.h2.b); q.w3 = W(L.h3.w); q.b3 = W(L.h3.b); q.w4 = W(L.h4.w); q.b4 = W(L.h4.b);
