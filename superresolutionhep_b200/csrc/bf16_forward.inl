@@ -17,12 +17,12 @@ EncodeTiledFn get_encode_fn() {
 }
 
 // bf16 row-major [rows, cols] with row pitch ld (elements); box = 64 columns x 128 rows, 128B swizzle
-int make_a_tmap(SrhepHandle* h, CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld) {
+int make_a_tmap(SrhepHandle* h, CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows = kGemmBM) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return fail(h, SRHEP_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t dims[2] = {cols, rows};
     cuuint64_t strides[1] = {ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)kGemmBK, (cuuint32_t)kGemmBM};
+    cuuint32_t box[2] = {(cuuint32_t)kGemmBK, (cuuint32_t)box_rows};
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(m, (h->precision == SRHEP_PREC_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -124,6 +124,8 @@ int bf16_pack_weights(SrhepHandle* h, const float* wh) {
     CK(h, cudaFuncSetAttribute(gemm_bf16_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_bf16_smem_bytes<256>(4)));
     CK(h, cudaFuncSetAttribute(gemm_bf16_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_bf16_smem_bytes<256>(4)));
     CK(h, cudaFuncSetAttribute(attn_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmemBytes));
+    CK(h, cudaFuncSetAttribute(attn2_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAtt2SmemBytes));
+    CK(h, cudaFuncSetAttribute(attn2_bf16_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CK(h, cudaFuncSetAttribute(head_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeadSmemBytes));
     CK(h, cudaFuncSetAttribute(layer_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemBytes));
     CK(h, cudaFuncSetAttribute(layer_chain_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -145,12 +147,14 @@ int bf16_on_bind(SrhepHandle* h) {
     const uint64_t R = h->cap_ws_rows;
     if (bw.tok_lp) { CK(h, cudaFree(bw.tok_lp)); bw.tok_lp = nullptr; }
     CK(h, cudaMalloc(&bw.tok_lp, R * bw.feat0_kpad * 2));
+    CK(h, cudaMemset(bw.tok_lp, 0, R * bw.feat0_kpad * 2));      // the K padding columns stay zero; the embedding kernel writes the rest
     int rc;
     if ((rc = make_a_tmap(h, &bw.tm_ln, h->act_a, R, d.h_dim, d.h_dim))) return rc;
     if ((rc = make_a_tmap(h, &bw.tm_hin, h->act_a, R, d.v_in + d.ctx, d.v_in + d.ctx))) return rc;
     if ((rc = make_a_tmap(h, &bw.tm_b, h->act_b, R, d.h_dim, d.h_dim))) return rc;
     if ((rc = make_a_tmap(h, &bw.tm_tok, bw.tok_lp, R, bw.feat0_kpad, bw.feat0_kpad))) return rc;
     if ((rc = make_a_tmap(h, &bw.tm_qkv, h->qkv_lp, R, 3 * d.h_dim, 3 * d.h_dim))) return rc;
+    if ((rc = make_a_tmap(h, &bw.tm_kv64, h->qkv_lp, R, 3 * d.h_dim, 3 * d.h_dim, kAtt2KvTile))) return rc;
     return 0;
 }
 
@@ -181,9 +185,27 @@ void launch_attn_bf16(Engine& E, const Pass& p, __nv_bfloat16* out) {
     q.out = out; q.ldo = d.h_dim; q.h_dim = d.h_dim;
     q.scale_log2 = 1.4426950408889634f / sqrtf((float)(d.h_dim / d.heads));
     q.fp16 = h->precision == SRHEP_PREC_FP16;
+    q.dbg = nullptr;
+    static long long* adbg = nullptr;
+    static int adbg_calls = 0;
+    const bool dbg = getenv("SRHEP_ATTN_DBG") && (++adbg_calls == 8);
+    if (dbg) { if (!adbg) cudaMalloc(&adbg, 256 * sizeof(long long)); cudaMemsetAsync(adbg, 0, 256 * sizeof(long long), E.s); q.dbg = adbg; }
     dim3 grid(std::max(1, std::min(q.n_items, 2 * 148 / d.heads)), d.heads);
+    if (!getenv("SRHEP_ATTN_V1")) attn2_bf16_kernel<<<grid, kAtt2Threads, kAtt2SmemBytes, E.s>>>(h->bw.tm_qkv, h->bw.tm_kv64, q);
+    else
     attn_bf16_kernel<<<grid, kAttnThreads, kAttnSmemBytes, E.s>>>(h->bw.tm_qkv, q);
     E.check("attn_bf16");
+    if (dbg) {
+        long long hb[256];
+        cudaStreamSynchronize(E.s);
+        cudaMemcpy(hb, adbg, sizeof hb, cudaMemcpyDeviceToHost);
+        const long long t0 = hb[0];
+        for (int i = 0; i < 4; ++i) {
+            fprintf(stderr, "[attn dbg] item %d:", i);
+            for (int k = 0; k < 64; ++k) if (hb[i * 64 + k]) fprintf(stderr, " %d=%lld", k, hb[i * 64 + k] - t0);
+            fprintf(stderr, "\n");
+        }
+    }
 }
 
 // One launch for the row-local part of DiT layer l: out-projection ... q|k|v of layer l + 1 (kernels_chain.cuh)
@@ -244,12 +266,7 @@ void bf16_forward(Engine& E, const Pass& p, const int* rev, const StageRef& st) 
     E.x_blocked = chain;
     __nv_bfloat16* a = (__nv_bfloat16*)h->act_a; __nv_bfloat16* b = (__nv_bfloat16*)h->act_b;
     __nv_bfloat16* qkv = (__nv_bfloat16*)h->qkv_lp;
-    E.cat = SRHEP_CAT_FEAT0;
-    if (!E.rc) {
-        const int grid = (int)std::min<size_t>(((size_t)M * bw.feat0_kpad + 255) / 256, 148 * 16);
-        cast_pad_bf16_kernel<<<grid, 256, 0, E.s>>>(h->tok_feat, ncol, bw.tok_lp, bw.feat0_kpad, M, ncol, fp16);
-        E.check("cast_pad_bf16");
-    }
+    E.cat = SRHEP_CAT_FEAT0;      // the 16-bit A operand of feat_0 was written by the embedding kernel
     // LayerNorm + adaLN modulate of the freshly produced residual row is fused into the epilogue of the GEMM
     // that produces it: ln1 of layer l rides on feat_0 (l = 0) / the previous layer's MLP2, ln2 on the out-projection.
     auto with_ln = [&](GemmEpilogue& ep, int layer, bool second) {

@@ -683,6 +683,7 @@ struct AttnBf16Params {
     int h_dim;                        // column offsets: q = head*64, k = h_dim + head*64, v = 2*h_dim + head*64
     float scale_log2;                 // log2(e) / sqrt(head_dim)
     int fp16;                         // 0 = bf16, 1 = fp16 operands / output
+    long long* dbg;                   // optional timeline of CTA (0, 0): clock64 stamps, 64 per item, first 4 items; null in production
 };
 
 __global__ void __launch_bounds__(kAttnThreads, 2) attn_bf16_kernel(const __grid_constant__ CUtensorMap tmap_qkv, AttnBf16Params p) {
@@ -911,7 +912,8 @@ struct Bf16Weights {
     __nv_bfloat16* tok_lp = nullptr; // [rows, feat0 K padded] bf16 copy of tok_feat (feat_0 GEMM A operand)
     int feat0_kpad = 0;
     CUtensorMap tm_ln, tm_hin, tm_b, tm_tok;      // A-operand maps over the pass workspace
-    CUtensorMap tm_qkv;                           // q|k|v tiles for the attention kernel
+    CUtensorMap tm_qkv;                           // q|k|v tiles for the attention kernel (128-row boxes)
+    CUtensorMap tm_kv64;                          // same matrix, 64-row boxes (key/value tiles of the second-generation attention)
 };
 
 }  // namespace srhep

@@ -154,113 +154,137 @@ struct EmbedTokParams {
     const float *eta, *cosphi, *sinphi, *e_proxy; const int* layer;
     StageRef stage;                      // x_in: pass-local rows
     int row0;                            // first global row of the pass
-    int chunk0;                          // first global chunk of the pass
+    int chunk0, chunk1;                  // global chunk range of the pass
     const float* ev_a; const float* ev_stats; const float* layer_out;
     const int *chunk_event, *chunk_row, *chunk_len;
     float* tok_feat; int ld;
     float* partial;
+    void* tok_lp; int ld_lp; int lp_fp16;   // optional 16-bit copy (row pitch ld_lp): the feat_0 GEMM's A operand
 };
 
 __global__ void __launch_bounds__(192) embed_tokens_kernel(EmbedTokParams p) {
     __shared__ float s_x[kChunk][5];                 // eta, cosphi, sinphi, e_proxy, x_t
     __shared__ int   s_layer[kChunk];
     __shared__ float s_mu[kChunk][3], s_rs[kChunk][3];
-    __shared__ float s_hid[kChunk][3 * kMaxHid + 1];
+    __shared__ __align__(16) float s_hid[kChunk][3 * kMaxHid + 4];     // rows 16-byte aligned: hidden vectors are read as float4 broadcasts
     const int tid = threadIdx.x;
-    const int c = p.chunk0 + blockIdx.x;
-    const int e = p.chunk_event[c], r0 = p.chunk_row[c], len = p.chunk_len[c];
     const float* x_in = load_stage(p.stage).x_in;
-
-    for (int i = tid; i < len * 6; i += blockDim.x) {
-        const int tok = i / 6, f = i % 6;
-        const size_t r = (size_t)r0 + tok;
-        if (f == 0) s_x[tok][0] = p.eta[r];
-        else if (f == 1) s_x[tok][1] = p.cosphi[r];
-        else if (f == 2) s_x[tok][2] = p.sinphi[r];
-        else if (f == 3) s_x[tok][3] = p.e_proxy[r];
-        else if (f == 4) s_x[tok][4] = x_in[r - p.row0];
-        else s_layer[tok] = p.layer[r];
-    }
-    __syncthreads();
-    const float mt = p.ev_stats[2 * (size_t)e], vt = p.ev_stats[2 * (size_t)e + 1];
     const float te = (float)p.t_emb;
-    for (int i = tid; i < len * 3; i += blockDim.x) {
-        const int tok = i / 3, n = i % 3;
-        float mu, q;
-        if (n == 0) {
-            const float a = s_x[tok][0], b = s_x[tok][1], cc = s_x[tok][2];
-            const float nf = 3.f + te;
-            mu = (a + b + cc + te * mt) / nf;
-            q = vt + te * (mt - mu) * (mt - mu) + (a - mu) * (a - mu) + (b - mu) * (b - mu) + (cc - mu) * (cc - mu);
-            q /= nf;
-        } else {
-            const float a = s_x[tok][n == 1 ? 3 : 4];
-            const float nf = 1.f + te;
-            mu = (a + te * mt) / nf;
-            q = (vt + te * (mt - mu) * (mt - mu) + (a - mu) * (a - mu)) / nf;
-        }
-        s_mu[tok][n] = mu;
-        s_rs[tok][n] = 1.0f / sqrtf(q + kLnEps);
+
+    // Persistent CTA: everything that depends only on the thread's role is loaded ONCE and reused for every chunk.
+    // (a) hidden unit `tid` of net n: first-layer weights of the per-cell inputs
+    const int hn = tid / kMaxHid, hj = tid % kMaxHid;
+    const EmbedNetDev& hnet = hn == 0 ? p.etaphi : (hn == 1 ? p.proxy : p.noisy);
+    const bool hid_on = tid < 3 * kMaxHid && hj < hnet.hid;
+    float hr1 = 0.f, hb1 = 0.f, hw0 = 0.f, hw1 = 0.f, hw2 = 0.f;
+    if (hid_on) {
+        hr1 = __ldg(hnet.r1 + hj); hb1 = __ldg(hnet.b1 + hj);
+        const float* w = hnet.w1 + (size_t)hj * (hnet.d + p.t_emb);
+        hw0 = __ldg(w); hw1 = hn == 0 ? __ldg(w + 1) : 0.f; hw2 = hn == 0 ? __ldg(w + 2) : 0.f;
     }
-    __syncthreads();
-    // hidden activations of the three per-cell nets
-    for (int idx = tid; idx < 3 * kMaxHid; idx += blockDim.x) {
-        const int n = idx / kMaxHid, j = idx % kMaxHid;
-        const EmbedNetDev& net = n == 0 ? p.etaphi : (n == 1 ? p.proxy : p.noisy);
-        if (j >= net.hid) continue;
-        const float a = p.ev_a[((size_t)e * 3 + n) * kMaxHid + j];
-        const float r1 = __ldg(net.r1 + j), b1 = __ldg(net.b1 + j);
-        const float* w = net.w1 + (size_t)j * (net.d + p.t_emb);
-        const float w0 = __ldg(w), w1 = n == 0 ? __ldg(w + 1) : 0.f, w2 = n == 0 ? __ldg(w + 2) : 0.f;
-        for (int tok = 0; tok < len; ++tok) {
-            const float mu = s_mu[tok][n];
-            float acc = a - mu * r1;
-            if (n == 0) {
-                acc = fmaf(w0, s_x[tok][0] - mu, acc);
-                acc = fmaf(w1, s_x[tok][1] - mu, acc);
-                acc = fmaf(w2, s_x[tok][2] - mu, acc);
-            } else {
-                acc = fmaf(w0, s_x[tok][n == 1 ? 3 : 4] - mu, acc);
-            }
-            s_hid[tok][idx] = leaky_relu(fmaf(s_rs[tok][n], acc, b1));
-        }
-    }
-    __syncthreads();
-    // output columns: one thread per column, weights of its row in registers
+    // (b) output column `tid`: its row of the second Linear in registers
     const int col = tid;
+    const int eo = p.etaphi.out, lo = p.layer_out_dim, po = p.proxy.out;
+    int kind = 3, o = 0, hoff = 0;                       // kind: 0 net, 1 layer gather, 2 raw e_proxy, 3 idle
+    const EmbedNetDev* net = nullptr;
     if (col < p.ncol) {
-        const int eo = p.etaphi.out, lo = p.layer_out_dim, po = p.proxy.out;
-        int kind, o = 0, hoff = 0;                       // kind: 0 net, 1 layer gather, 2 raw e_proxy
-        const EmbedNetDev* net = nullptr;
         if (col < eo)                { kind = 0; net = &p.etaphi; o = col;            hoff = 0; }
         else if (col < eo + lo)      { kind = 1; o = col - eo; }
         else if (col < eo + lo + po) { kind = 0; net = &p.proxy;  o = col - eo - lo;  hoff = kMaxHid; }
         else if (col < p.cond)       { kind = 2; }
         else                         { kind = 0; net = &p.noisy;  o = col - p.cond;   hoff = 2 * kMaxHid; }
-        float w[kMaxHid];
-        float b2 = 0.f;
-        if (kind == 0) {
+    }
+    float w[kMaxHid];
+    float b2 = 0.f;
+    if (kind == 0) {
 #pragma unroll
-            for (int j = 0; j < kMaxHid; ++j) w[j] = j < net->hid ? __ldg(net->w2 + (size_t)o * net->hid + j) : 0.f;
-            b2 = __ldg(net->b2 + o);
+        for (int j = 0; j < kMaxHid; ++j) w[j] = j < net->hid ? __ldg(net->w2 + (size_t)o * net->hid + j) : 0.f;
+        b2 = __ldg(net->b2 + o);
+    } else {
+#pragma unroll
+        for (int j = 0; j < kMaxHid; ++j) w[j] = 0.f;
+    }
+
+    for (int c = p.chunk0 + blockIdx.x; c < p.chunk1; c += gridDim.x) {
+        const int e = p.chunk_event[c], r0 = p.chunk_row[c], len = p.chunk_len[c];
+        __syncthreads();                                 // the previous chunk's readers are done with the shared tiles
+        for (int i = tid; i < len * 6; i += blockDim.x) {
+            const int tok = i / 6, f = i % 6;
+            const size_t r = (size_t)r0 + tok;
+            if (f == 0) s_x[tok][0] = p.eta[r];
+            else if (f == 1) s_x[tok][1] = p.cosphi[r];
+            else if (f == 2) s_x[tok][2] = p.sinphi[r];
+            else if (f == 3) s_x[tok][3] = p.e_proxy[r];
+            else if (f == 4) s_x[tok][4] = x_in[r - p.row0];
+            else s_layer[tok] = p.layer[r];
         }
-        float colsum = 0.f;
-        for (int tok = 0; tok < len; ++tok) {
-            float val;
-            if (kind == 0) {
-                float acc = b2;
-#pragma unroll
-                for (int j = 0; j < kMaxHid; ++j) acc = fmaf(w[j], s_hid[tok][hoff + j], acc);
-                val = leaky_relu(acc);
-            } else if (kind == 1) {
-                val = p.layer_out[((size_t)e * 3 + s_layer[tok]) * lo + o];
+        __syncthreads();
+        const float mt = p.ev_stats[2 * (size_t)e], vt = p.ev_stats[2 * (size_t)e + 1];
+        for (int i = tid; i < len * 3; i += blockDim.x) {
+            const int tok = i / 3, n = i % 3;
+            float mu, q;
+            if (n == 0) {
+                const float a = s_x[tok][0], b = s_x[tok][1], cc = s_x[tok][2];
+                const float nf = 3.f + te;
+                mu = (a + b + cc + te * mt) / nf;
+                q = vt + te * (mt - mu) * (mt - mu) + (a - mu) * (a - mu) + (b - mu) * (b - mu) + (cc - mu) * (cc - mu);
+                q /= nf;
             } else {
-                val = s_x[tok][3];
+                const float a = s_x[tok][n == 1 ? 3 : 4];
+                const float nf = 1.f + te;
+                mu = (a + te * mt) / nf;
+                q = (vt + te * (mt - mu) * (mt - mu) + (a - mu) * (a - mu)) / nf;
             }
-            p.tok_feat[((size_t)(r0 - p.row0) + tok) * p.ld + col] = val;
-            colsum += val;
+            s_mu[tok][n] = mu;
+            s_rs[tok][n] = 1.0f / sqrtf(q + kLnEps);
         }
-        if (col < p.cond) p.partial[(size_t)c * p.cond + col] = colsum;
+        __syncthreads();
+        // hidden activations of the three per-cell nets
+        if (hid_on) {
+            const float a = p.ev_a[((size_t)e * 3 + hn) * kMaxHid + hj];
+            for (int tok = 0; tok < len; ++tok) {
+                const float mu = s_mu[tok][hn];
+                float acc = a - mu * hr1;
+                if (hn == 0) {
+                    acc = fmaf(hw0, s_x[tok][0] - mu, acc);
+                    acc = fmaf(hw1, s_x[tok][1] - mu, acc);
+                    acc = fmaf(hw2, s_x[tok][2] - mu, acc);
+                } else {
+                    acc = fmaf(hw0, s_x[tok][hn == 1 ? 3 : 4] - mu, acc);
+                }
+                s_hid[tok][tid] = leaky_relu(fmaf(s_rs[tok][hn], acc, hb1));
+            }
+        }
+        __syncthreads();
+        // output columns: one thread per column
+        if (kind != 3) {
+            float colsum = 0.f;
+            for (int tok = 0; tok < len; ++tok) {
+                float val;
+                if (kind == 0) {
+                    float acc = b2;
+                    const float4* h4 = reinterpret_cast<const float4*>(&s_hid[tok][hoff]);
+#pragma unroll
+                    for (int j = 0; j < kMaxHid; j += 4) {
+                        const float4 hv = h4[j >> 2];
+                        acc = fmaf(w[j], hv.x, acc); acc = fmaf(w[j + 1], hv.y, acc); acc = fmaf(w[j + 2], hv.z, acc); acc = fmaf(w[j + 3], hv.w, acc);
+                    }
+                    val = leaky_relu(acc);
+                } else if (kind == 1) {
+                    val = p.layer_out[((size_t)e * 3 + s_layer[tok]) * lo + o];
+                } else {
+                    val = s_x[tok][3];
+                }
+                p.tok_feat[((size_t)(r0 - p.row0) + tok) * p.ld + col] = val;
+                if (p.tok_lp) {
+                    const size_t o16 = ((size_t)(r0 - p.row0) + tok) * p.ld_lp + col;
+                    if (p.lp_fp16) reinterpret_cast<__half*>(p.tok_lp)[o16] = __float2half_rn(val);
+                    else reinterpret_cast<__nv_bfloat16*>(p.tok_lp)[o16] = __float2bfloat16_rn(val);
+                }
+                colsum += val;
+            }
+            if (col < p.cond) p.partial[(size_t)c * p.cond + col] = colsum;
+        }
     }
 }
 

@@ -20,6 +20,7 @@
 #include "kernels_bf16.cuh"
 #include "kernels_chain.cuh"
 #include "kernels_head.cuh"
+#include "kernels_attn.cuh"
 
 using namespace srhep;
 
@@ -332,11 +333,12 @@ struct Engine {
             q.noisy = net(L.nsy1, L.nsy3, 1, 3);
             q.layer_out_dim = d.layer_out; q.t_emb = d.t_emb; q.cond = d.cond; q.ncol = ncol;
             q.eta = h->cond.eta; q.cosphi = h->cond.cosphi; q.sinphi = h->cond.sinphi; q.e_proxy = h->cond.e_proxy; q.layer = h->cond.layer;
-            q.stage = st; q.row0 = p.r0; q.chunk0 = p.c0;
+            q.stage = st; q.row0 = p.r0; q.chunk0 = p.c0; q.chunk1 = p.c1;
             q.ev_a = h->ev_a; q.ev_stats = h->ev_stats; q.layer_out = h->layer_out;
             q.chunk_event = h->chunk_event; q.chunk_row = h->chunk_row; q.chunk_len = h->chunk_len;
             q.tok_feat = h->tok_feat; q.ld = ncol; q.partial = h->partial;
-            if (!rc) { embed_tokens_kernel<<<p.c1 - p.c0, 192, 0, s>>>(q); check("embed_tokens"); }
+            q.tok_lp = lp ? (void*)h->bw.tok_lp : nullptr; q.ld_lp = h->bw.feat0_kpad; q.lp_fp16 = h->precision == SRHEP_PREC_FP16;
+            if (!rc) { embed_tokens_kernel<<<std::min(p.c1 - p.c0, 148 * 8), 192, 0, s>>>(q); check("embed_tokens"); }
         }
         {   // 3. context
             ContextParams q;
