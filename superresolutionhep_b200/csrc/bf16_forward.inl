@@ -124,8 +124,10 @@ int bf16_pack_weights(SrhepHandle* h, const float* wh) {
     CK(h, cudaFuncSetAttribute(gemm_bf16_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_bf16_smem_bytes<256>(4)));
     CK(h, cudaFuncSetAttribute(gemm_bf16_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_bf16_smem_bytes<256>(4)));
     CK(h, cudaFuncSetAttribute(attn_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmemBytes));
-    CK(h, cudaFuncSetAttribute(attn2_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAtt2SmemBytes));
-    CK(h, cudaFuncSetAttribute(attn2_bf16_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(h, cudaFuncSetAttribute(attn2_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAtt2SmemBytes));
+    CK(h, cudaFuncSetAttribute(attn2_bf16_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(h, cudaFuncSetAttribute(attn2_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAtt2SmemBytes));
+    CK(h, cudaFuncSetAttribute(attn2_bf16_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CK(h, cudaFuncSetAttribute(head_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeadSmemBytes));
     CK(h, cudaFuncSetAttribute(layer_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemBytes));
     CK(h, cudaFuncSetAttribute(layer_chain_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -191,7 +193,10 @@ void launch_attn_bf16(Engine& E, const Pass& p, __nv_bfloat16* out) {
     const bool dbg = getenv("SRHEP_ATTN_DBG") && (++adbg_calls == 8);
     if (dbg) { if (!adbg) cudaMalloc(&adbg, 256 * sizeof(long long)); cudaMemsetAsync(adbg, 0, 256 * sizeof(long long), E.s); q.dbg = adbg; }
     dim3 grid(std::max(1, std::min(q.n_items, 2 * 148 / d.heads)), d.heads);
-    if (!getenv("SRHEP_ATTN_V1")) attn2_bf16_kernel<<<grid, kAtt2Threads, kAtt2SmemBytes, E.s>>>(h->bw.tm_qkv, h->bw.tm_kv64, q);
+    if (!getenv("SRHEP_ATTN_V1")) {
+        if (q.fp16) attn2_bf16_kernel<true><<<grid, kAtt2Threads, kAtt2SmemBytes, E.s>>>(h->bw.tm_qkv, h->bw.tm_kv64, q);
+        else attn2_bf16_kernel<false><<<grid, kAtt2Threads, kAtt2SmemBytes, E.s>>>(h->bw.tm_qkv, h->bw.tm_kv64, q);
+    }
     else
     attn_bf16_kernel<<<grid, kAttnThreads, kAttnSmemBytes, E.s>>>(h->bw.tm_qkv, q);
     E.check("attn_bf16");

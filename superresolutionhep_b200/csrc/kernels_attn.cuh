@@ -27,6 +27,7 @@ constexpr size_t kAtt2SmemBytes = kAtt2OffBars + 256;                     // 2 C
 
 #define ATT_STAMP(item, k) do { if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && (item) < 4 && (k) < 64) p.dbg[(item) * 64 + (k)] = clock64(); } while (0)
 
+template <bool kFp16>
 __global__ void __launch_bounds__(kAtt2Threads, 2) attn2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                                                                      AttnBf16Params p) {
     extern __shared__ __align__(1024) uint8_t attn2_smem[];
@@ -87,8 +88,8 @@ __global__ void __launch_bounds__(kAtt2Threads, 2) attn2_bf16_kernel(const __gri
             }
         }
     } else if (warp == 1) {
-        const uint32_t idesc_s = umma_idesc_16(128, 64, p.fp16);               // S = Q K^T
-        const uint32_t idesc_o = umma_idesc_16(128, 64, p.fp16) | (1u << 16);  // O = P V (V MN-major)
+        const uint32_t idesc_s = umma_idesc_16(128, 64, kFp16 ? 1 : 0);        // S = Q K^T
+        const uint32_t idesc_o = umma_idesc_16(128, 64, kFp16 ? 1 : 0) | (1u << 16);  // O = P V (V MN-major)
         uint32_t it = 0, item_i = 0;
         auto issue_s = [&](uint32_t t, bool last_of_item) {                    // t = global key-tile counter
             const uint32_t s = t % kAtt2Stages, ph = (t / kAtt2Stages) & 1, b = t & 1;
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(kAtt2Threads, 2) attn2_bf16_kernel(const __gri
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-        const int fp16 = p.fp16;
+        constexpr int fp16 = kFp16 ? 1 : 0;
         uint32_t it = 0, item_i = 0;
         for (int w = blockIdx.x; w < p.n_items; w += gridDim.x, ++item_i) {
             const AttnItem a = p.items[w];
@@ -174,23 +175,25 @@ __global__ void __launch_bounds__(kAtt2Threads, 2) attn2_bf16_kernel(const __gri
                     m_ref = mx;
                 }
                 uint32_t pk[32];
-                float l4[4] = {0.f, 0.f, 0.f, 0.f};
-                const float sc = p.scale_log2, nm = -m_ref;
+                const uint64_t sc2 = pack_f32x2(p.scale_log2, p.scale_log2), nm2 = pack_f32x2(-m_ref, -m_ref);
+                uint64_t l2a = 0ull, l2b = 0ull;                            // two packed running sums = four independent chains
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {                          // exp2(-inf) = 0 takes care of the masked keys
-                    const float e0 = fast_exp2(fmaf(__uint_as_float(r0[i]), sc, nm)), e1 = fast_exp2(fmaf(__uint_as_float(r0[i + 1]), sc, nm));
-                    const float e2 = fast_exp2(fmaf(__uint_as_float(r0[i + 2]), sc, nm)), e3 = fast_exp2(fmaf(__uint_as_float(r0[i + 3]), sc, nm));
-                    l4[0] += e0; l4[1] += e1; l4[2] += e2; l4[3] += e3;
+                    const uint64_t t0 = ffma2(pack_f32x2(__uint_as_float(r0[i]), __uint_as_float(r0[i + 1])), sc2, nm2);
+                    const uint64_t t1 = ffma2(pack_f32x2(__uint_as_float(r0[i + 2]), __uint_as_float(r0[i + 3])), sc2, nm2);
+                    const float e0 = fast_exp2(f32x2_lo(t0)), e1 = fast_exp2(f32x2_hi(t0)), e2 = fast_exp2(f32x2_lo(t1)), e3 = fast_exp2(f32x2_hi(t1));
+                    l2a = fadd2(l2a, pack_f32x2(e0, e1)); l2b = fadd2(l2b, pack_f32x2(e2, e3));
                     pk[i >> 1] = pack16(e0, e1, fp16); pk[(i >> 1) + 1] = pack16(e2, e3, fp16);
                 }
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
-                    const float e0 = fast_exp2(fmaf(__uint_as_float(r1[i]), sc, nm)), e1 = fast_exp2(fmaf(__uint_as_float(r1[i + 1]), sc, nm));
-                    const float e2 = fast_exp2(fmaf(__uint_as_float(r1[i + 2]), sc, nm)), e3 = fast_exp2(fmaf(__uint_as_float(r1[i + 3]), sc, nm));
-                    l4[0] += e0; l4[1] += e1; l4[2] += e2; l4[3] += e3;
+                    const uint64_t t0 = ffma2(pack_f32x2(__uint_as_float(r1[i]), __uint_as_float(r1[i + 1])), sc2, nm2);
+                    const uint64_t t1 = ffma2(pack_f32x2(__uint_as_float(r1[i + 2]), __uint_as_float(r1[i + 3])), sc2, nm2);
+                    const float e0 = fast_exp2(f32x2_lo(t0)), e1 = fast_exp2(f32x2_hi(t0)), e2 = fast_exp2(f32x2_lo(t1)), e3 = fast_exp2(f32x2_hi(t1));
+                    l2a = fadd2(l2a, pack_f32x2(e0, e1)); l2b = fadd2(l2b, pack_f32x2(e2, e3));
                     pk[16 + (i >> 1)] = pack16(e0, e1, fp16); pk[17 + (i >> 1)] = pack16(e2, e3, fp16);
                 }
-                l = fmaf(l, corr, (l4[0] + l4[1]) + (l4[2] + l4[3]));
+                l = fmaf(l, corr, (f32x2_lo(l2a) + f32x2_hi(l2a)) + (f32x2_lo(l2b) + f32x2_hi(l2b)));
                 // the P buffer is free once PV of tile it - 2 retired
                 if (it >= 2) mbar_wait(&pv_done[b], ((it >> 1) - 1) & 1);
                 uint8_t* prow = s_p + b * 16384 + row * 128;

@@ -140,6 +140,13 @@ __device__ __forceinline__ void stg256(void* p, const uint32_t* v) {
     asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                  ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
 }
+// packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2, two fp32 lanes per issue slot)
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) { return (uint64_t)__float_as_uint(lo) | ((uint64_t)__float_as_uint(hi) << 32); }
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) { uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ float f32x2_lo(uint64_t v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float f32x2_hi(uint64_t v) { return __uint_as_float((uint32_t)(v >> 32)); }
+
 // streaming variants: do not allocate in L1 (keeps the small L1 for the per-event / per-column parameter rows)
 __device__ __forceinline__ void ldg256_stream(const float* p, float* d) {
     asm volatile("ld.global.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"

@@ -124,6 +124,12 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
 #pragma unroll
                         for (int kb = 0; kb < 4; ++kb) tma_load_2d(s_a + kb * 16384, &tmap_a, a_full, kb * 64, t * 128);
                         CHAIN_STAMP(tile_i, 1);
+                        // the fp32 residual tile of THIS tile (128 KB contiguous in the blocked layout) is first needed by the
+                        // stage-0 epilogue, several microseconds from now: pull it into L2 meanwhile
+                        const float* xt = p.x + (size_t)t * 128 * kChainH;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(xt + i * 8192), "r"(32768u) : "memory");
                     }
                     const int g = j >> 3, kb = (j >> 1) & 3, nh = j & 1;
                     const uint32_t s = slot_it % kChainSlots, ph = (slot_it / kChainSlots) & 1;
