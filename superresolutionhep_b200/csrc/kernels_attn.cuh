@@ -25,7 +25,11 @@ constexpr uint32_t kAtt2OffP = kAtt2OffKv + kAtt2Stages * 16384;         // 2 x 
 constexpr uint32_t kAtt2OffBars = kAtt2OffP + 2 * 16384;
 constexpr size_t kAtt2SmemBytes = kAtt2OffBars + 256;                     // 2 CTAs per SM
 
+#ifdef SRHEP_TIMELINE
 #define ATT_STAMP(item, k) do { if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && (item) < 4 && (k) < 64) p.dbg[(item) * 64 + (k)] = clock64(); } while (0)
+#else
+#define ATT_STAMP(item, k) do { } while (0)
+#endif
 
 template <bool kFp16>
 __global__ void __launch_bounds__(kAtt2Threads, 2) attn2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,

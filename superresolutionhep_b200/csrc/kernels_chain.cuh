@@ -78,7 +78,11 @@ __device__ __forceinline__ void chain_store_a(uint8_t* s_a, int rt, int col0, co
                        pack16(v[8 * g + 4], v[8 * g + 5], fp16), pack16(v[8 * g + 6], v[8 * g + 7], fp16));
 }
 
+#ifdef SRHEP_TIMELINE      // build with -DSRHEP_TIMELINE to record the CTA timeline (tools/chain_dbg.py); costs registers, off in production
 #define CHAIN_STAMP(tile, k) do { if (p.dbg && blockIdx.x == 0 && (tile) < 8) p.dbg[(tile) * 32 + (k)] = clock64(); } while (0)
+#else
+#define CHAIN_STAMP(tile, k) do { } while (0)
+#endif
 
 __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ ChainParams p) {
     extern __shared__ __align__(1024) uint8_t chain_smem[];      // no static smem in this kernel: the dynamic window starts 1024-aligned
@@ -189,8 +193,9 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
             const int row = t * 128 + rt;
             const bool valid = row < p.M;
             const int evt = valid ? p.row_event[row] : 0;
-            float* xrow = p.x + xblk_index(row, hh * 128);         // + 1024 floats per 8-column group (32 B pieces of this row)
-            const size_t eo = (size_t)evt * p.ld_mod + hh * 128;
+            const uint32_t xoff = (uint32_t)xblk_index(row, hh * 128);   // 32-bit element offsets keep the epilogue under its register budget
+#define xrow (p.x + xoff)                                         /* + 1024 floats per 8-column group (32 B pieces of this row) */
+            const uint32_t eo = (uint32_t)evt * (uint32_t)p.ld_mod + hh * 128;
             constexpr float inv_n = 1.0f / (float)kChainH;
 
             // ---------------------------------------------------------------- stage 0: out-projection, residual, LN2 + modulate + LN
@@ -384,5 +389,7 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
     __syncthreads();
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
 }
+
+#undef xrow
 
 }  // namespace srhep
