@@ -41,6 +41,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     cmd = [nvcc, *NVCC_FLAGS, "-o", LIB, os.path.join(CSRC, "srhep.cu")]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
+    if os.environ.get("SRHEP_POLY_MASK"):
+        cmd.insert(1, "-DSRHEP_POLY_MASK=" + os.environ["SRHEP_POLY_MASK"])
     if os.environ.get("SRHEP_TIMELINE"):
         cmd.insert(1, "-DSRHEP_TIMELINE")
     r = subprocess.run(cmd, capture_output=True, text=True)

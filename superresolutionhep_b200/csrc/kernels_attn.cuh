@@ -20,6 +20,10 @@ namespace srhep {
 constexpr int kAtt2Threads = 192;
 constexpr int kAtt2Stages = 4;
 constexpr int kAtt2KvTile = 64;
+#ifndef SRHEP_POLY_MASK
+#define SRHEP_POLY_MASK 0xAA
+#endif
+constexpr int kPolyMask = SRHEP_POLY_MASK;          // which of the 8 groups of 4 scores per 32 use the polynomial exp2 for their second pair (0xAA: every other group = 25 %)
 constexpr uint32_t kAtt2OffKv = 16384;                                   // after Q
 constexpr uint32_t kAtt2OffP = kAtt2OffKv + kAtt2Stages * 16384;         // 2 x 16 KB
 constexpr uint32_t kAtt2OffBars = kAtt2OffP + 2 * 16384;
@@ -185,7 +189,10 @@ __global__ void __launch_bounds__(kAtt2Threads, 2) attn2_bf16_kernel(const __gri
                 for (int i = 0; i < 32; i += 4) {                          // exp2(-inf) = 0 takes care of the masked keys
                     const uint64_t t0 = ffma2(pack_f32x2(__uint_as_float(r0[i]), __uint_as_float(r0[i + 1])), sc2, nm2);
                     const uint64_t t1 = ffma2(pack_f32x2(__uint_as_float(r0[i + 2]), __uint_as_float(r0[i + 3])), sc2, nm2);
-                    const float e0 = fast_exp2(f32x2_lo(t0)), e1 = fast_exp2(f32x2_hi(t0)), e2 = fast_exp2(f32x2_lo(t1)), e3 = fast_exp2(f32x2_hi(t1));
+                    const float e0 = fast_exp2(f32x2_lo(t0)), e1 = fast_exp2(f32x2_hi(t0));
+                    float e2, e3;
+                    if (kPolyMask & (1 << ((i >> 2) & 7))) exp2_poly_x2(t1, e2, e3);     // part of the exponentials leave the SFU for the FMA pipe
+                    else { e2 = fast_exp2(f32x2_lo(t1)); e3 = fast_exp2(f32x2_hi(t1)); }
                     l2a = fadd2(l2a, pack_f32x2(e0, e1)); l2b = fadd2(l2b, pack_f32x2(e2, e3));
                     pk[i >> 1] = pack16(e0, e1, fp16); pk[(i >> 1) + 1] = pack16(e2, e3, fp16);
                 }
@@ -193,7 +200,10 @@ __global__ void __launch_bounds__(kAtt2Threads, 2) attn2_bf16_kernel(const __gri
                 for (int i = 0; i < 32; i += 4) {
                     const uint64_t t0 = ffma2(pack_f32x2(__uint_as_float(r1[i]), __uint_as_float(r1[i + 1])), sc2, nm2);
                     const uint64_t t1 = ffma2(pack_f32x2(__uint_as_float(r1[i + 2]), __uint_as_float(r1[i + 3])), sc2, nm2);
-                    const float e0 = fast_exp2(f32x2_lo(t0)), e1 = fast_exp2(f32x2_hi(t0)), e2 = fast_exp2(f32x2_lo(t1)), e3 = fast_exp2(f32x2_hi(t1));
+                    const float e0 = fast_exp2(f32x2_lo(t0)), e1 = fast_exp2(f32x2_hi(t0));
+                    float e2, e3;
+                    if (kPolyMask & (1 << ((i >> 2) & 7))) exp2_poly_x2(t1, e2, e3);
+                    else { e2 = fast_exp2(f32x2_lo(t1)); e3 = fast_exp2(f32x2_hi(t1)); }
                     l2a = fadd2(l2a, pack_f32x2(e0, e1)); l2b = fadd2(l2b, pack_f32x2(e2, e3));
                     pk[16 + (i >> 1)] = pack16(e0, e1, fp16); pk[17 + (i >> 1)] = pack16(e2, e3, fp16);
                 }
