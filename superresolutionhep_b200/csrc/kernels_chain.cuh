@@ -54,7 +54,7 @@ __device__ __forceinline__ void chain_resid_chunk(uint32_t (&r)[32], const float
                                                   const float* __restrict__ gate, float& s1, float& s2) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
-        const float4 g4 = *reinterpret_cast<const float4*>(gate + j);
+        const float4 g4 = ldg128_stream(gate + j);           // the tiny L1 is left to the register spills
         const float bb[4] = {bias[j], bias[j + 1], bias[j + 2], bias[j + 3]}, gg[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -67,16 +67,19 @@ __device__ __forceinline__ void chain_resid_chunk(uint32_t (&r)[32], const float
     }
 }
 
-// 32 consecutive values of row `rt` -> 16-bit, into the K-major 128B-swizzled A buffer at columns [col0, col0 + 32)
-__device__ __forceinline__ void chain_store_a(uint8_t* s_a, int rt, int col0, const float (&v)[32], int fp16) {
-    uint8_t* arow = s_a + (col0 >> 6) * 16384 + rt * 128;
+// 32 consecutive values of row `rt` -> 16-bit, into the K-major 128B-swizzled A buffer (32-bit shared address
+// `a_addr`) at columns [col0, col0 + 32)
+__device__ __forceinline__ void chain_store_a(uint32_t a_addr, int rt, int col0, const float (&v)[32], int fp16) {
+    const uint32_t arow = a_addr + (uint32_t)((col0 >> 6) * 16384 + rt * 128);
     const int cb = (col0 & 63) >> 3;
 #pragma unroll
     for (int g = 0; g < 4; ++g)
-        *reinterpret_cast<uint4*>(arow + (((cb + g) ^ (rt & 7)) << 4)) =
-            make_uint4(pack16(v[8 * g], v[8 * g + 1], fp16), pack16(v[8 * g + 2], v[8 * g + 3], fp16),
-                       pack16(v[8 * g + 4], v[8 * g + 5], fp16), pack16(v[8 * g + 6], v[8 * g + 7], fp16));
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(arow + (uint32_t)(((cb + g) ^ (rt & 7)) << 4)),
+                     "r"(pack16(v[8 * g], v[8 * g + 1], fp16)), "r"(pack16(v[8 * g + 2], v[8 * g + 3], fp16)),
+                     "r"(pack16(v[8 * g + 4], v[8 * g + 5], fp16)), "r"(pack16(v[8 * g + 6], v[8 * g + 7], fp16)) : "memory");
 }
+__device__ __forceinline__ void sts_f2(uint32_t addr, float a, float b) { asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory"); }
+__device__ __forceinline__ float2 lds_f2(uint32_t addr) { float2 v; asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory"); return v; }
 
 #ifdef SRHEP_TIMELINE      // build with -DSRHEP_TIMELINE to record the CTA timeline (tools/chain_dbg.py); costs registers, off in production
 #define CHAIN_STAMP(tile, k) do { if (p.dbg && blockIdx.x == 0 && (tile) < 8) p.dbg[(tile) * 32 + (k)] = clock64(); } while (0)
@@ -94,9 +97,10 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
     uint64_t* a_free = bars + 1;         // MMA -> TMA      last MMA of the tile retired: A may be overwritten
     uint64_t* w_full = bars + 2;         // [slots] TMA -> MMA
     uint64_t* w_empty = bars + 5;        // [slots] MMA -> TMA
-    uint64_t* acc_full = bars + 8;       // MMA -> epilogue  accumulator of a stage complete
-    uint64_t* epi_done = bars + 9;       // epilogue -> MMA  accumulator drained (and A rewritten)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+    uint64_t* acc_full = bars + 8;       // [2] MMA -> epilogue  one 128-column half of a stage's accumulator complete
+    uint64_t* epi_done = bars + 10;      // [2] epilogue -> MMA  the 4 warps of a column half are done with their half of TMEM
+    uint64_t* a_written = bars + 12;     // epilogue -> MMA  all 8 warps rewrote the A operand (stages that feed another GEMM)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tiles = (p.M + 127) / 128;
@@ -107,7 +111,8 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
         prefetch_tmap(&tmap_a);
         mbar_init(a_full, 1); mbar_init(a_free, 1);
         for (int i = 0; i < kChainSlots; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-        mbar_init(acc_full, 1); mbar_init(epi_done, 8);
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&epi_done[i], 4); }
+        mbar_init(a_written, 8);
         mbar_fence_init();
     }
     if (warp == 1) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
@@ -135,7 +140,7 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                         for (int i = 0; i < 4; ++i)
                             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(xt + i * 8192), "r"(32768u) : "memory");
                     }
-                    const int g = j >> 3, kb = (j >> 1) & 3, nh = j & 1;
+                    const int g = j >> 3, nh = (j >> 2) & 1, kb = j & 3;      // column half outer: the two halves of the accumulator are a double buffer
                     const uint32_t s = slot_it % kChainSlots, ph = (slot_it / kChainSlots) & 1;
                     mbar_wait(&w_empty[s], ph ^ 1);
                     mbar_expect_tx(&w_full[s], kChainSlotBytes);
@@ -145,30 +150,35 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
         }
     } else if (warp == 1) {
         const uint32_t idesc = umma_idesc_16(128, 128, p.fp16);
-        uint32_t slot_it = 0, stage_it = 0, tile_i = 0;
+        uint32_t slot_it = 0, stage_it = 0, tile_i = 0, aw_it = 0;
         for (int t = blockIdx.x; t < m_tiles; t += gridDim.x, ++tile_i) {
             for (int g = 0; g < p.n_stages; ++g, ++stage_it) {
-                if (stage_it > 0) mbar_wait(epi_done, (stage_it - 1) & 1);      // accumulator drained, A operand of this stage in place
-                if (g == 0) { if (lane == 0) CHAIN_STAMP(tile_i, 2); mbar_wait(a_full, tile_i & 1); if (lane == 0) CHAIN_STAMP(tile_i, 3); }
-                tc_fence_after();
-                for (int j = 0; j < 8; ++j, ++slot_it) {
-                    const int kb = j >> 1, nh = j & 1;
-                    const uint32_t s = slot_it % kChainSlots, ph = (slot_it / kChainSlots) & 1;
-                    mbar_wait(&w_full[s], ph);
-                    tc_fence_after();
-                    if (elect_one()) {
-                        const uint32_t a_addr = smem_u32(s_a + kb * 16384), b_addr = smem_u32(s_w + s * kChainSlotBytes);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            umma_bf16(tmem_base + nh * 128, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
-                                      (uint32_t)((kb | k) != 0));
-                        tc_commit(&w_empty[s]);
-                        if (j == 7) {
-                            tc_commit(acc_full);
-                            if (g == p.n_stages - 1) tc_commit(a_free);
-                        }
+                for (int nh = 0; nh < 2; ++nh) {
+                    // this half of the accumulator was drained by the previous stage's epilogue (its 4 warps)
+                    if (stage_it > 0) mbar_wait(&epi_done[nh], (stage_it - 1) & 1);
+                    if (nh == 0) {
+                        if (g == 0) { if (lane == 0) CHAIN_STAMP(tile_i, 2); mbar_wait(a_full, tile_i & 1); if (lane == 0) CHAIN_STAMP(tile_i, 3); }
+                        else if (g <= 3) { mbar_wait(a_written, aw_it & 1); ++aw_it; }      // stages 1-3 read the A operand the previous epilogue wrote
                     }
-                    __syncwarp();
+                    tc_fence_after();
+                    for (int kb = 0; kb < 4; ++kb, ++slot_it) {
+                        const uint32_t s = slot_it % kChainSlots, ph = (slot_it / kChainSlots) & 1;
+                        mbar_wait(&w_full[s], ph);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint32_t a_addr = smem_u32(s_a + kb * 16384), b_addr = smem_u32(s_w + s * kChainSlotBytes);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_bf16(tmem_base + nh * 128, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                                          (uint32_t)((kb | k) != 0));
+                            tc_commit(&w_empty[s]);
+                            if (kb == 3) {
+                                tc_commit(&acc_full[nh]);
+                                if (nh == 1 && g == p.n_stages - 1) tc_commit(a_free);
+                            }
+                        }
+                        __syncwarp();
+                    }
                 }
                 if (lane == 0) CHAIN_STAMP(tile_i, 4 + g);
             }
@@ -177,16 +187,16 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
         const int q = warp & 3, hh = (warp - 2) >> 2;
         const int rt = q * 32 + lane;                                  // row inside the tile = TMEM lane
         const uint32_t t_col = tmem_base + ((uint32_t)(q * 32) << 16) + hh * 128;
-        float2* st1 = reinterpret_cast<float2*>(s_a);                  // LayerNorm partial sums: scratch inside the (then dead) A buffer
-        float2* st2 = st1 + 256;
+        const uint32_t a_sh = smem_u32(s_a);                            // 32-bit shared addresses keep the epilogue inside its register budget
+        const uint32_t st_own = a_sh + (uint32_t)(hh * 128 + rt) * 8, st_oth = a_sh + (uint32_t)((hh ^ 1) * 128 + rt) * 8;   // LayerNorm partial sums: scratch in the (then dead) A buffer
         const int fp16 = p.fp16;
         uint32_t stage_it = 0, tile_i = 0;
-        auto stage_done = [&]() {
+        auto stage_done = [&](bool wrote_a) {
             if (warp == 2 && lane == 0) CHAIN_STAMP(tile_i, 11 + 2 * (int)(stage_it % (uint32_t)p.n_stages));
             fence_async_smem();                                        // A stores -> visible to the tensor-core (async) proxy
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(epi_done);
+            if (lane == 0) { mbar_arrive(&epi_done[hh]); if (wrote_a) mbar_arrive(a_written); }
             ++stage_it;
         };
         for (int t = blockIdx.x; t < m_tiles; t += gridDim.x, ++tile_i) {
@@ -207,7 +217,7 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) ldg256_stream(xrow + (j >> 3) * 1024, &xr[j]);   // in flight while the MMAs run
                 }
-                mbar_wait(acc_full, stage_it & 1);
+                mbar_wait(&acc_full[hh], stage_it & 1);
                 if (warp == 2 && lane == 0) CHAIN_STAMP(tile_i, 10);
                 tc_fence_after();
                 float s1 = 0.f, s2 = 0.f;
@@ -229,10 +239,11 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                 }
                 if (warp == 2 && lane == 0) CHAIN_STAMP(tile_i, 22);
                 tmem_st_wait();
-                st1[hh * 128 + rt] = make_float2(s1, s2);
+                mbar_wait(&acc_full[hh ^ 1], stage_it & 1);               // the other half's MMAs still read the A buffer, which holds the scratch below
+                sts_f2(st_own, s1, s2);
                 named_bar_sync(1, 256);
                 if (warp == 2 && lane == 0) CHAIN_STAMP(tile_i, 23);
-                const float2 o1 = st1[(hh ^ 1) * 128 + rt];
+                const float2 o1 = lds_f2(st_oth);
                 float mean = (s1 + o1.x) * inv_n;
                 float rstd = rsqrtf(fmaxf((s2 + o1.y) * inv_n - mean * mean, 0.f) + kLnEps);
                 float t1 = 0.f, t2 = 0.f;
@@ -245,7 +256,7 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                     const float* sc = p.scale_mlp + eo + c * 32; const float* sh = p.shift_mlp + eo + c * 32;
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
-                        const float4 s4 = *reinterpret_cast<const float4*>(sc + j), h4 = *reinterpret_cast<const float4*>(sh + j);
+                        const float4 s4 = ldg128_stream(sc + j), h4 = ldg128_stream(sh + j);
                         const float ww[4] = {lw[j], lw[j + 1], lw[j + 2], lw[j + 3]}, bb[4] = {lb[j], lb[j + 1], lb[j + 2], lb[j + 3]};
                         const float ss[4] = {s4.x, s4.y, s4.z, s4.w}, hs[4] = {h4.x, h4.y, h4.z, h4.w};
 #pragma unroll
@@ -260,9 +271,9 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                 }
                 if (warp == 2 && lane == 0) CHAIN_STAMP(tile_i, 24);
                 tmem_st_wait();
-                st2[hh * 128 + rt] = make_float2(t1, t2);
+                sts_f2(st_own + 2048, t1, t2);
                 named_bar_sync(1, 256);
-                const float2 o2 = st2[(hh ^ 1) * 128 + rt];
+                const float2 o2 = lds_f2(st_oth + 2048);
                 mean = (t1 + o2.x) * inv_n;
                 rstd = rsqrtf(fmaxf((t2 + o2.y) * inv_n - mean * mean, 0.f) + kLnEps);
                 named_bar_sync(1, 256);                                  // every thread has read its partner's sums: the scratch may be overwritten
@@ -275,13 +286,14 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = (__uint_as_float(r[j]) - mean) * rstd;
-                    chain_store_a(s_a, rt, hh * 128 + c * 32, v, fp16);
+                    chain_store_a(a_sh, rt, hh * 128 + c * 32, v, fp16);
                 }
-                stage_done();
+                stage_done(true);
             }
             // ---------------------------------------------------------------- stage 1: MLP hidden
             {
-                mbar_wait(acc_full, stage_it & 1);
+                mbar_wait(&acc_full[hh], stage_it & 1);
+                mbar_wait(&acc_full[hh ^ 1], stage_it & 1);               // A is rewritten in place: every MMA of the stage must have retired
                 if (warp == 2 && lane == 0) CHAIN_STAMP(tile_i, 12);
                 tc_fence_after();
 #pragma unroll 1
@@ -293,9 +305,9 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = leaky_relu(__uint_as_float(r[j]) + b[j]);
-                    chain_store_a(s_a, rt, hh * 128 + c * 32, v, fp16);
+                    chain_store_a(a_sh, rt, hh * 128 + c * 32, v, fp16);
                 }
-                stage_done();
+                stage_done(true);
             }
             // ---------------------------------------------------------------- stage 2: MLP output, residual, next layer's LN1 + modulate
             {
@@ -307,7 +319,7 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) ldg256_stream(xrow + (j >> 3) * 1024, &xr[j]);   // x1, written by this thread in stage 0
                 }
-                mbar_wait(acc_full, stage_it & 1);
+                mbar_wait(&acc_full[hh], stage_it & 1);
                 if (warp == 2 && lane == 0) CHAIN_STAMP(tile_i, 14);
                 tc_fence_after();
                 float s1 = 0.f, s2 = 0.f;
@@ -329,9 +341,10 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                 }
                 if (next) {
                     tmem_st_wait();
-                    st1[hh * 128 + rt] = make_float2(s1, s2);
+                    mbar_wait(&acc_full[hh ^ 1], stage_it & 1);
+                    sts_f2(st_own, s1, s2);
                     named_bar_sync(1, 256);
-                    const float2 o1 = st1[(hh ^ 1) * 128 + rt];
+                    const float2 o1 = lds_f2(st_oth);
                     const float mean = (s1 + o1.x) * inv_n;
                     const float rstd = rsqrtf(fmaxf((s2 + o1.y) * inv_n - mean * mean, 0.f) + kLnEps);
                     named_bar_sync(1, 256);
@@ -345,7 +358,7 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                         float v[32];
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
-                            const float4 s4 = *reinterpret_cast<const float4*>(sc + j), h4 = *reinterpret_cast<const float4*>(sh + j);
+                            const float4 s4 = ldg128_stream(sc + j), h4 = ldg128_stream(sh + j);
                             const float ww[4] = {lw[j], lw[j + 1], lw[j + 2], lw[j + 3]}, bb[4] = {lb[j], lb[j + 1], lb[j + 2], lb[j + 3]};
                             const float ss[4] = {s4.x, s4.y, s4.z, s4.w}, hs[4] = {h4.x, h4.y, h4.z, h4.w};
 #pragma unroll
@@ -354,16 +367,16 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                                 v[j + u] = fmaf(y, 1.f + ss[u], hs[u]);
                             }
                         }
-                        chain_store_a(s_a, rt, hh * 128 + c * 32, v, fp16);
+                        chain_store_a(a_sh, rt, hh * 128 + c * 32, v, fp16);
                     }
                 }
-                stage_done();
+                stage_done(next);
             }
             // ---------------------------------------------------------------- stages 3-5: q, k, v of the next layer
             if (p.n_stages > 3) {
 #pragma unroll 1
                 for (int g = 0; g < 3; ++g) {
-                    mbar_wait(acc_full, stage_it & 1);
+                    mbar_wait(&acc_full[hh], stage_it & 1);
                     if (warp == 2 && lane == 0) CHAIN_STAMP(tile_i, 16 + 2 * g);
                     tc_fence_after();
                     uint16_t* dst = reinterpret_cast<uint16_t*>(p.qkv) + (size_t)row * (3 * kChainH) + g * kChainH + hh * 128;
@@ -380,7 +393,7 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                             stg256(dst + c * 32, &pk[0]); stg256(dst + c * 32 + 16, &pk[8]);
                         }
                     }
-                    stage_done();
+                    stage_done(false);
                 }
             }
         }

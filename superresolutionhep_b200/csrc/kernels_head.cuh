@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_chain_kernel(const __gri
                     float w[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) w[i] = v[c * 32 + i];
-                    chain_store_a(s_a2, rt, c * 32, w, fp16);
+                    chain_store_a(smem_u32(s_a2), rt, c * 32, w, fp16);
                 }
                 fence_async_smem();
                 __syncwarp();
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_chain_kernel(const __gri
                     float w[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) w[i] = (v[c * 32 + i] - mean) * rstd;
-                    chain_store_a(s_a3, rt, c * 32, w, fp16);
+                    chain_store_a(smem_u32(s_a3), rt, c * 32, w, fp16);
                 }
                 fence_async_smem();
                 tc_fence_before();
