@@ -129,8 +129,10 @@ int bf16_pack_weights(SrhepHandle* h, const float* wh) {
     CK(h, cudaFuncSetAttribute(attn2_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAtt2SmemBytes));
     CK(h, cudaFuncSetAttribute(attn2_bf16_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CK(h, cudaFuncSetAttribute(head_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeadSmemBytes));
-    CK(h, cudaFuncSetAttribute(layer_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemBytes));
-    CK(h, cudaFuncSetAttribute(layer_chain_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(h, cudaFuncSetAttribute(layer_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemBytes));
+    CK(h, cudaFuncSetAttribute(layer_chain_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(h, cudaFuncSetAttribute(layer_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemBytes));
+    CK(h, cudaFuncSetAttribute(layer_chain_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CK(h, cudaFuncSetAttribute(gemm_bf16_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_bf16_smem_bytes<128>(hk / 64)));
     return 0;
 }
@@ -243,7 +245,8 @@ void launch_chain(Engine& E, int M, int l, const int* rev) {
     static long long* dbg_dev = nullptr;
     const bool dbg = getenv("SRHEP_CHAIN_DBG") && l == 1;
     if (dbg) { if (!dbg_dev) cudaMalloc(&dbg_dev, 256 * sizeof(long long)); cudaMemsetAsync(dbg_dev, 0, 256 * sizeof(long long), E.s); q.dbg = dbg_dev; }
-    layer_chain_kernel<<<grid, kChainThreads, kChainSmemBytes, E.s>>>(bw.tm_b, q);
+    if (q.fp16) layer_chain_kernel<true><<<grid, kChainThreads, kChainSmemBytes, E.s>>>(bw.tm_b, q);
+    else layer_chain_kernel<false><<<grid, kChainThreads, kChainSmemBytes, E.s>>>(bw.tm_b, q);
     E.check("layer_chain");
     if (dbg) {
         long long hbuf[256];

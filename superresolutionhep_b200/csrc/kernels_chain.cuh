@@ -87,6 +87,7 @@ __device__ __forceinline__ float2 lds_f2(uint32_t addr) { float2 v; asm volatile
 #define CHAIN_STAMP(tile, k) do { } while (0)
 #endif
 
+template <bool kFp16>
 __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ ChainParams p) {
     extern __shared__ __align__(1024) uint8_t chain_smem[];      // no static smem in this kernel: the dynamic window starts 1024-aligned
     uint8_t* s_a = chain_smem;
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
             }
         }
     } else if (warp == 1) {
-        const uint32_t idesc = umma_idesc_16(128, 128, p.fp16);
+        const uint32_t idesc = umma_idesc_16(128, 128, kFp16 ? 1 : 0);
         uint32_t slot_it = 0, stage_it = 0, tile_i = 0, aw_it = 0;
         for (int t = blockIdx.x; t < m_tiles; t += gridDim.x, ++tile_i) {
             for (int g = 0; g < p.n_stages; ++g, ++stage_it) {
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
         const uint32_t t_col = tmem_base + ((uint32_t)(q * 32) << 16) + hh * 128;
         const uint32_t a_sh = smem_u32(s_a);                            // 32-bit shared addresses keep the epilogue inside its register budget
         const uint32_t st_own = a_sh + (uint32_t)(hh * 128 + rt) * 8, st_oth = a_sh + (uint32_t)((hh ^ 1) * 128 + rt) * 8;   // LayerNorm partial sums: scratch in the (then dead) A buffer
-        const int fp16 = p.fp16;
+        constexpr int fp16 = kFp16 ? 1 : 0;                            // compile-time operand format: one conversion per pair, no selects
         uint32_t stage_it = 0, tile_i = 0;
         auto stage_done = [&](bool wrote_a) {
             if (warp == 2 && lane == 0) CHAIN_STAMP(tile_i, 11 + 2 * (int)(stage_it % (uint32_t)p.n_stages));
