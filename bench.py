@@ -53,6 +53,19 @@ def flops_per_eval(counts: np.ndarray) -> float:
     return float((5088448.0 * n + 6144.0 * n * n + 3215360.0).sum())
 
 
+def load_traffic(workload, events, precision):
+    """DRAM bytes per launch of each kernel category from the committed ncu capture (profiles/), if it was taken
+    on this exact workload; None otherwise."""
+    p = os.path.join(ROOT, "profiles", "r01_kernel_traffic.json")
+    if not os.path.isfile(p):
+        return {}
+    with open(p) as fp:
+        d = json.load(fp)
+    if d.get("workload") != workload or d.get("events_per_gpu") != events or d.get("precision") != precision:
+        return {}
+    return d.get("dram_bytes_per_launch", {})
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -318,8 +331,8 @@ def main():
         achieved = algo[dom] / dom_launch / (dom_ms / dom_launch * 1e-3) / 1e12
         peak = peaks["tf_sustained"]
         roof = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": f"{peaks['source']} (sustained bf16, kernel timed inside a long step)",
-                "kernel_ms_per_launch": dom_ms / dom_launch, "share_of_evaluation": dom_ms / total_ms if total_ms else None,
+                "traffic": load_traffic(args.workload, B, args.precision).get(dom), "peak_source": f"{peaks['source']} (sustained bf16, kernel timed inside a long step)",
+                "kernel_ms_per_launch": dom_ms / dom_launch, "algorithmic_flops_per_launch": algo[dom] / dom_launch, "share_of_evaluation": dom_ms / total_ms if total_ms else None,
                 "per_category_ms": {c: round(per_cat[c]["ms"], 4) for c in per_cat},
                 "evaluation_tflops": flops_per_eval(counts) / (total_ms * 1e-3) / 1e12 if total_ms else None}
         cpu = None
