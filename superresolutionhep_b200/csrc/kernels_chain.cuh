@@ -81,6 +81,31 @@ __device__ __forceinline__ void chain_store_a(uint32_t a_addr, int rt, int col0,
 __device__ __forceinline__ void sts_f2(uint32_t addr, float a, float b) { asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory"); }
 __device__ __forceinline__ float2 lds_f2(uint32_t addr) { float2 v; asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory"); return v; }
 
+// Row-per-lane registers -> line-per-4-lanes registers.  In: a[32] = this lane's 128 bytes (one full line: 64 16-bit columns
+// of its row) as four 32-byte pieces.  Out: a[8 i .. 8 i + 7] = piece (lane & 3) of row (lane & ~3) + i, so that store i of the
+// warp writes 8 complete 128-byte lines (4 lanes each) instead of touching 32 different lines: a quarter of the LSU wavefronts.
+// Two butterfly rounds over the 4 lanes of a group (xor 2, xor 1); each shuffle swaps one register between the two partners.
+__device__ __forceinline__ void transpose_line_pieces(uint32_t (&a)[32], int lane) {
+    const bool b1 = (lane & 2) != 0, b0 = (lane & 1) != 0;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        const uint32_t send = b1 ? a[r] : a[16 + r];
+        const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 2);
+        a[r] = b1 ? recv : a[r];
+        a[16 + r] = b1 ? a[16 + r] : recv;
+    }
+#pragma unroll
+    for (int h = 0; h < 32; h += 16) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const uint32_t send = b0 ? a[h + r] : a[h + 8 + r];
+            const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
+            a[h + r] = b0 ? recv : a[h + r];
+            a[h + 8 + r] = b0 ? a[h + 8 + r] : recv;
+        }
+    }
+}
+
 #ifdef SRHEP_TIMELINE      // build with -DSRHEP_TIMELINE to record the CTA timeline (tools/chain_dbg.py); costs registers, off in production
 #define CHAIN_STAMP(tile, k) do { if (p.dbg && blockIdx.x == 0 && (tile) < 8) p.dbg[(tile) * 32 + (k)] = clock64(); } while (0)
 #else
@@ -380,19 +405,26 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                     mbar_wait(&acc_full[hh], stage_it & 1);
                     if (warp == 2 && lane == 0) CHAIN_STAMP(tile_i, 16 + 2 * g);
                     tc_fence_after();
-                    uint16_t* dst = reinterpret_cast<uint16_t*>(p.qkv) + (size_t)row * (3 * kChainH) + g * kChainH + hh * 128;
+                    // 64 columns (one 128-byte line per row) at a time: bias, pack, regroup across the 4 lanes of a group, store whole lines
+                    const int row4 = t * 128 + (rt & ~3);                                   // first row of this lane's group of four
+                    uint16_t* dst = reinterpret_cast<uint16_t*>(p.qkv) + (size_t)row4 * (3 * kChainH) + g * kChainH + hh * 128 + (lane & 3) * 16;
 #pragma unroll 1
-                    for (int c = 0; c < 4; ++c) {
-                        uint32_t r[32];
-                        tmem_ld32(t_col + c * 32, r);
-                        tmem_ld_wait();
-                        if (valid) {
-                            const float* b = &p.cst[3 + g][hh * 128 + c * 32];
-                            uint32_t pk[16];
+                    for (int blk = 0; blk < 2; ++blk) {
+                        uint32_t a[32];
 #pragma unroll
-                            for (int j = 0; j < 32; j += 2) pk[j >> 1] = pack16(__uint_as_float(r[j]) + b[j], __uint_as_float(r[j + 1]) + b[j + 1], fp16);
-                            stg256(dst + c * 32, &pk[0]); stg256(dst + c * 32 + 16, &pk[8]);
+                        for (int half = 0; half < 2; ++half) {
+                            const int c = blk * 2 + half;
+                            uint32_t r[32];
+                            tmem_ld32(t_col + c * 32, r);
+                            tmem_ld_wait();
+                            const float* b = &p.cst[3 + g][hh * 128 + c * 32];
+#pragma unroll
+                            for (int j = 0; j < 32; j += 2) a[half * 16 + (j >> 1)] = pack16(__uint_as_float(r[j]) + b[j], __uint_as_float(r[j + 1]) + b[j + 1], fp16);
                         }
+                        transpose_line_pieces(a, lane);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (row4 + i < p.M) stg256(dst + (size_t)i * (3 * kChainH) + blk * 64, &a[8 * i]);
                     }
                     stage_done(false);
                 }
