@@ -122,3 +122,28 @@ def test_sharding_and_passes_are_bit_exact(precision):
         sub = {k: (v[sl] if torch.is_tensor(v) else v) for k, v in batch.items()}
         part = m.generate_samples(to_dev(sub), n_steps=3, method="midpoint", x0=x0[sl].cuda()).cpu()
         assert torch.equal(part[mask[sl]], whole[sl][mask[sl]])
+
+
+def test_full_size_config2_properties():
+    """BASELINE.json configs[1] at full size (4096 single-electron events, bf16 tensor-core path): properties that
+    need no oracle.  Events are independent and every kernel is row-local or event-local, so (i) cutting the batch
+    into passes and (ii) permuting the events must reproduce every cell BIT FOR BIT; (iii) ``x_seq[0]`` is the
+    noise, ``ret_seq=False`` is the last state, everything is finite."""
+    m, sd, dims = make_model("single_e", 7, "bf16")
+    B = 4096
+    batch = synthetic_events("single_e", B, seed=1234)
+    x0 = synthetic_noise(batch, seed=0)
+    mask = batch["q_mask"]
+    xs = m.generate_samples(to_dev(batch), n_steps=3, method="euler", ret_seq=True, x0=x0.cuda())
+    assert xs.shape == (3, B, mask.shape[1], 1) and bool(torch.isfinite(xs).all())
+    assert torch.equal(xs[0].cpu(), x0)
+    last = m.generate_samples(to_dev(batch), n_steps=3, method="euler", x0=x0.cuda())
+    assert torch.equal(last[mask.cuda()], xs[-1][mask.cuda()])
+    m.pass_tokens = 300000                                                  # 4 passes instead of 1
+    cut = m.generate_samples(to_dev(batch), n_steps=3, method="euler", x0=x0.cuda())
+    assert torch.equal(cut[mask.cuda()], last[mask.cuda()])
+    m.pass_tokens = 0
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(5))
+    pb = {k: (v[perm] if torch.is_tensor(v) else v) for k, v in batch.items()}
+    pp = m.generate_samples(to_dev(pb), n_steps=3, method="euler", x0=x0[perm].cuda())
+    assert torch.equal(pp.cpu()[mask[perm]], last.cpu()[perm][mask[perm]])
