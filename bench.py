@@ -169,7 +169,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    _emit(line)
 
 
 def workload_config(args, events_per_gpu, precision):
@@ -180,6 +180,29 @@ def workload_config(args, events_per_gpu, precision):
 
 
 def main():
+    # Libraries (NCCL with NCCL_DEBUG=VERSION, torchrun banners) may write to stdout; the contract is ONE JSON line there.
+    # Everything before the final print goes to stderr.
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        _main()
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    if _RESULT_LINE is not None:
+        print(_RESULT_LINE, flush=True)
+
+
+_RESULT_LINE = None
+
+
+def _emit(line: dict) -> None:
+    global _RESULT_LINE
+    _RESULT_LINE = json.dumps(line)
+
+
+def _main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
@@ -355,7 +378,7 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line))
+        _emit(line)
 
 
 if __name__ == "__main__":
