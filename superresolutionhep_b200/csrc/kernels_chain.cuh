@@ -31,6 +31,7 @@ constexpr uint32_t kChainSlotBytes = 16384;          // 128 weight rows x 128 B
 constexpr uint32_t kChainABytes = 65536;             // 4 k-blocks x (128 rows x 128 B)
 constexpr size_t kChainSmemBytes = kChainABytes + kChainSlots * kChainSlotBytes + 128;
 constexpr int kChainH = 256;
+constexpr int kChainStageEv = 16;                    // events per tile whose adaLN rows are staged in shared memory (3 KB each, after the 4 KB statistics scratch)
 
 struct ChainParams {
     int M;                       // rows of this pass
@@ -48,13 +49,21 @@ struct ChainParams {
     long long* dbg;              // optional timeline of CTA 0 (clock64 stamps, 32 per tile, first 8 tiles); null in production
 };
 
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+// four consecutive values of a per-event adaLN row: from the copy staged in shared memory (the usual case) or from global memory
+__device__ __forceinline__ float4 par_f4(bool staged, uint32_t sm_addr, const float* g) { return staged ? lds_f4(sm_addr) : ldg128_stream(g); }
+
 // acc + bias (+ LeakyReLU), gated into the residual: returns the new residual chunk in r[] (as bits)
 template <bool kAct>
 __device__ __forceinline__ void chain_resid_chunk(uint32_t (&r)[32], const float (&xr)[32], const float* bias /*constant bank*/,
-                                                  const float* __restrict__ gate, float& s1, float& s2) {
+                                                  bool staged, uint32_t gate_sm, const float* __restrict__ gate, float& s1, float& s2) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
-        const float4 g4 = ldg128_stream(gate + j);           // the tiny L1 is left to the register spills
+        const float4 g4 = par_f4(staged, gate_sm + j * 4, gate + j);
         const float bb[4] = {bias[j], bias[j + 1], bias[j + 2], bias[j + 3]}, gg[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -63,6 +72,24 @@ __device__ __forceinline__ void chain_resid_chunk(uint32_t (&r)[32], const float
             w = fmaf(gg[u], w, xr[j + u]);
             s1 += w; s2 = fmaf(w, w, s2);
             r[j + u] = __float_as_uint(w);
+        }
+    }
+}
+
+// r[] (bits of the residual row chunk) -> (LN(r) * w + b) * (1 + scale) + shift in place; accumulates sum / sum of squares of the result
+__device__ __forceinline__ void chain_ln_mod_chunk(uint32_t (&r)[32], float mean, float rstd, const float* lw, const float* lb /*constant bank*/,
+                                                   bool staged, uint32_t sc_sm, uint32_t sh_sm, const float* __restrict__ sc, const float* __restrict__ sh,
+                                                   float& t1, float& t2) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+        const float4 s4 = par_f4(staged, sc_sm + j * 4, sc + j), h4 = par_f4(staged, sh_sm + j * 4, sh + j);
+        const float ss[4] = {s4.x, s4.y, s4.z, s4.w}, hs[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float y = fmaf((__uint_as_float(r[j + u]) - mean) * rstd, lw[j + u], lb[j + u]);
+            y = fmaf(y, 1.f + ss[u], hs[u]);
+            t1 += y; t2 = fmaf(y, y, t2);
+            r[j + u] = __float_as_uint(y);
         }
     }
 }
@@ -126,7 +153,8 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
     uint64_t* acc_full = bars + 8;       // [2] MMA -> epilogue  one 128-column half of a stage's accumulator complete
     uint64_t* epi_done = bars + 10;      // [2] epilogue -> MMA  the 4 warps of a column half are done with their half of TMEM
     uint64_t* a_written = bars + 12;     // epilogue -> MMA  all 8 warps rewrote the A operand (stages that feed another GEMM)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+    uint64_t* par_full = bars + 13;      // bulk copies of the tile's per-event adaLN rows landed in the (dead) A buffer
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tiles = (p.M + 127) / 128;
@@ -138,7 +166,7 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
         mbar_init(a_full, 1); mbar_init(a_free, 1);
         for (int i = 0; i < kChainSlots; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&epi_done[i], 4); }
-        mbar_init(a_written, 8);
+        mbar_init(a_written, 8); mbar_init(par_full, 1);
         mbar_fence_init();
     }
     if (warp == 1) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
@@ -225,14 +253,39 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
             if (lane == 0) { mbar_arrive(&epi_done[hh]); if (wrote_a) mbar_arrive(a_written); }
             ++stage_it;
         };
+        uint32_t par_it = 0;
+        const uint32_t par_sh = a_sh + 4096;                           // staged adaLN rows: [event in tile][3 arrays][256 floats]
         for (int t = blockIdx.x; t < m_tiles; t += gridDim.x, ++tile_i) {
             const int row = t * 128 + rt;
             const bool valid = row < p.M;
-            const int evt = valid ? p.row_event[row] : 0;
+            const int ev0 = p.row_event[t * 128];
+            const int ne = p.row_event[min(t * 128 + 127, p.M - 1)] - ev0 + 1;
+            const bool staged = ne <= kChainStageEv;                   // CTA-uniform
+            const int evt = valid ? p.row_event[row] : ev0;
             const uint32_t xoff = (uint32_t)xblk_index(row, hh * 128);   // 32-bit element offsets keep the epilogue under its register budget
 #define xrow (p.x + xoff)                                         /* + 1024 floats per 8-column group (32 B pieces of this row) */
             const uint32_t eo = (uint32_t)evt * (uint32_t)p.ld_mod + hh * 128;
+            const uint32_t psm = par_sh + (uint32_t)(evt - ev0) * 3072 + hh * 512;       // this row's event, this thread's column half, array 0
             constexpr float inv_n = 1.0f / (float)kChainH;
+            // One thread copies the tile's per-event rows of three adaLN arrays into the A buffer once every MMA of the stage has
+            // retired (the buffer is dead until this stage's last pass rewrites it); everybody then reads them as shared-memory
+            // broadcasts instead of paying an L2 round trip per 32-column chunk.
+            auto stage_rows = [&](const float* a0, const float* a1, const float* a2) {
+                if (!staged) return;
+                if (warp == 2 && lane == 0) {
+                    const int na = 1 + (a1 != nullptr) + (a2 != nullptr);
+                    mbar_expect_tx(par_full, (uint32_t)(ne * na) * 1024u);
+                    for (int e = 0; e < ne; ++e) {
+                        const size_t go = (size_t)(ev0 + e) * p.ld_mod;
+                        uint8_t* dst = s_a + 4096 + e * 3072;
+                        bulk_load(dst, a0 + go, 1024, par_full);
+                        if (a1) bulk_load(dst + 1024, a1 + go, 1024, par_full);
+                        if (a2) bulk_load(dst + 2048, a2 + go, 1024, par_full);
+                    }
+                }
+                mbar_wait(par_full, par_it & 1);
+                ++par_it;
+            };
 
             // ---------------------------------------------------------------- stage 0: out-projection, residual, LN2 + modulate + LN
             {
@@ -244,15 +297,17 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                     for (int j = 0; j < 32; j += 8) ldg256_stream(xrow + (j >> 3) * 1024, &xr[j]);   // in flight while the MMAs run
                 }
                 mbar_wait(&acc_full[hh], stage_it & 1);
+                mbar_wait(&acc_full[hh ^ 1], stage_it & 1);               // every MMA of the stage retired: the A buffer is free for the scratch and the staged rows
                 if (warp == 2 && lane == 0) CHAIN_STAMP(tile_i, 10);
                 tc_fence_after();
+                stage_rows(p.gate_msa, p.scale_mlp, p.shift_mlp);
                 float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
                     uint32_t r[32];
                     tmem_ld32(t_col + c * 32, r);
                     tmem_ld_wait();
-                    chain_resid_chunk<false>(r, xr, &p.cst[0][hh * 128 + c * 32], p.gate_msa + eo + c * 32, s1, s2);
+                    chain_resid_chunk<false>(r, xr, &p.cst[0][hh * 128 + c * 32], staged, psm + c * 128, p.gate_msa + eo + c * 32, s1, s2);
                     if (valid) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 8) stg256_stream(xrow + (c * 4 + (j >> 3)) * 1024, &r[j]);
@@ -265,7 +320,6 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                 }
                 if (warp == 2 && lane == 0) CHAIN_STAMP(tile_i, 22);
                 tmem_st_wait();
-                mbar_wait(&acc_full[hh ^ 1], stage_it & 1);               // the other half's MMAs still read the A buffer, which holds the scratch below
                 sts_f2(st_own, s1, s2);
                 named_bar_sync(1, 256);
                 if (warp == 2 && lane == 0) CHAIN_STAMP(tile_i, 23);
@@ -278,21 +332,8 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                     uint32_t r[32];
                     tmem_ld32(t_col + c * 32, r);
                     tmem_ld_wait();
-                    const float* lw = &p.cst[6][hh * 128 + c * 32]; const float* lb = &p.cst[7][hh * 128 + c * 32];
-                    const float* sc = p.scale_mlp + eo + c * 32; const float* sh = p.shift_mlp + eo + c * 32;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 s4 = ldg128_stream(sc + j), h4 = ldg128_stream(sh + j);
-                        const float ww[4] = {lw[j], lw[j + 1], lw[j + 2], lw[j + 3]}, bb[4] = {lb[j], lb[j + 1], lb[j + 2], lb[j + 3]};
-                        const float ss[4] = {s4.x, s4.y, s4.z, s4.w}, hs[4] = {h4.x, h4.y, h4.z, h4.w};
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            float y = fmaf((__uint_as_float(r[j + u]) - mean) * rstd, ww[u], bb[u]);
-                            y = fmaf(y, 1.f + ss[u], hs[u]);
-                            t1 += y; t2 = fmaf(y, y, t2);
-                            r[j + u] = __float_as_uint(y);
-                        }
-                    }
+                    chain_ln_mod_chunk(r, mean, rstd, &p.cst[6][hh * 128 + c * 32], &p.cst[7][hh * 128 + c * 32], staged, psm + 1024 + c * 128, psm + 2048 + c * 128,
+                                       p.scale_mlp + eo + c * 32, p.shift_mlp + eo + c * 32, t1, t2);
                     tmem_st32(t_col + c * 32, r);
                 }
                 if (warp == 2 && lane == 0) CHAIN_STAMP(tile_i, 24);
@@ -302,7 +343,7 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                 const float2 o2 = lds_f2(st_oth + 2048);
                 mean = (t1 + o2.x) * inv_n;
                 rstd = rsqrtf(fmaxf((t2 + o2.y) * inv_n - mean * mean, 0.f) + kLnEps);
-                named_bar_sync(1, 256);                                  // every thread has read its partner's sums: the scratch may be overwritten
+                named_bar_sync(1, 256);                                  // every thread has read its partner's sums and the staged rows: the buffer may be overwritten
                 if (warp == 2 && lane == 0) CHAIN_STAMP(tile_i, 25);
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {                            // the Dense's own non-affine LayerNorm (models/dense.py:62) -> A
@@ -346,15 +387,19 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                     for (int j = 0; j < 32; j += 8) ldg256_stream(xrow + (j >> 3) * 1024, &xr[j]);   // x1, written by this thread in stage 0
                 }
                 mbar_wait(&acc_full[hh], stage_it & 1);
+                mbar_wait(&acc_full[hh ^ 1], stage_it & 1);
                 if (warp == 2 && lane == 0) CHAIN_STAMP(tile_i, 14);
                 tc_fence_after();
+                // last layer: the A buffer is handed back to the producer (a_free) as soon as this stage's MMAs retire, so nothing may be staged in it
+                const bool st2 = staged && next;
+                if (st2) stage_rows(p.gate_mlp, p.scale_nxt, p.shift_nxt);
                 float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
                     uint32_t r[32];
                     tmem_ld32(t_col + c * 32, r);
                     tmem_ld_wait();
-                    chain_resid_chunk<true>(r, xr, &p.cst[2][hh * 128 + c * 32], p.gate_mlp + eo + c * 32, s1, s2);
+                    chain_resid_chunk<true>(r, xr, &p.cst[2][hh * 128 + c * 32], st2, psm + c * 128, p.gate_mlp + eo + c * 32, s1, s2);
                     if (valid) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 8) stg256_stream(xrow + (c * 4 + (j >> 3)) * 1024, &r[j]);
@@ -367,32 +412,31 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                 }
                 if (next) {
                     tmem_st_wait();
-                    mbar_wait(&acc_full[hh ^ 1], stage_it & 1);
                     sts_f2(st_own, s1, s2);
                     named_bar_sync(1, 256);
                     const float2 o1 = lds_f2(st_oth);
                     const float mean = (s1 + o1.x) * inv_n;
                     const float rstd = rsqrtf(fmaxf((s2 + o1.y) * inv_n - mean * mean, 0.f) + kLnEps);
-                    named_bar_sync(1, 256);
+                    float t1 = 0.f, t2 = 0.f;
+#pragma unroll 1
+                    for (int c = 0; c < 4; ++c) {                        // next layer's LN1 affine + modulate, parked in TMEM (the staged rows are still being read)
+                        uint32_t r[32];
+                        tmem_ld32(t_col + c * 32, r);
+                        tmem_ld_wait();
+                        chain_ln_mod_chunk(r, mean, rstd, &p.cst[8][hh * 128 + c * 32], &p.cst[9][hh * 128 + c * 32], staged, psm + 1024 + c * 128, psm + 2048 + c * 128,
+                                           p.scale_nxt + eo + c * 32, p.shift_nxt + eo + c * 32, t1, t2);
+                        tmem_st32(t_col + c * 32, r);
+                    }
+                    tmem_st_wait();
+                    named_bar_sync(1, 256);                              // all reads of the scratch and the staged rows are done: A may be rewritten
 #pragma unroll 1
                     for (int c = 0; c < 4; ++c) {
                         uint32_t r[32];
                         tmem_ld32(t_col + c * 32, r);
                         tmem_ld_wait();
-                        const float* lw = &p.cst[8][hh * 128 + c * 32]; const float* lb = &p.cst[9][hh * 128 + c * 32];
-                        const float* sc = p.scale_nxt + eo + c * 32; const float* sh = p.shift_nxt + eo + c * 32;
                         float v[32];
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 s4 = ldg128_stream(sc + j), h4 = ldg128_stream(sh + j);
-                            const float ww[4] = {lw[j], lw[j + 1], lw[j + 2], lw[j + 3]}, bb[4] = {lb[j], lb[j + 1], lb[j + 2], lb[j + 3]};
-                            const float ss[4] = {s4.x, s4.y, s4.z, s4.w}, hs[4] = {h4.x, h4.y, h4.z, h4.w};
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const float y = fmaf((__uint_as_float(r[j + u]) - mean) * rstd, ww[u], bb[u]);
-                                v[j + u] = fmaf(y, 1.f + ss[u], hs[u]);
-                            }
-                        }
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
                         chain_store_a(a_sh, rt, hh * 128 + c * 32, v, fp16);
                     }
                 }
