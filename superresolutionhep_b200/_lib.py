@@ -40,6 +40,18 @@ class PflowVarTransformC(C.Structure):
                 ("min", C.c_float), ("max", C.c_float), ("lo", C.c_float), ("hi", C.c_float)]
 
 
+POST_EXPORTS = ("srpost_ensemble_unscale", "srpost_select_cells", "srpost_last_error")
+
+
+class SrpostTargetTransformC(C.Structure):
+    """Mirror of ``SrpostTargetTransform`` in include/srhep_post.h."""
+    _fields_ = [("standard", C.c_int32), ("mean", C.c_float), ("std", C.c_float), ("alpha", C.c_float), ("f", C.c_float)]
+
+
+class SrpostPflowOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("e", "eta", "cosphi", "sinphi", "phi", "e_raw", "eta_raw", "layer")]
+
+
 class PflowCells(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("e", "eta", "cosphi", "sinphi", "phi", "e_raw", "eta_raw", "layer")]
 
@@ -101,8 +113,21 @@ def load() -> C.CDLL:
     lib.pflow_forward.argtypes = [vp, C.POINTER(PflowCells), vp, i32, vp, vp, vp, vp, vp, vp]
     lib.pflow_launch_count.restype = u64
     lib.pflow_launch_count.argtypes = [vp]
+    lib.srpost_ensemble_unscale.restype = C.c_int
+    lib.srpost_ensemble_unscale.argtypes = [vp, i32, i32, i64, vp, C.POINTER(SrpostTargetTransformC), f32, vp, vp, vp, vp]
+    lib.srpost_select_cells.restype = C.c_int
+    lib.srpost_select_cells.argtypes = [vp, vp, vp, vp, vp, i32, f32, C.POINTER(PflowVarTransformC), C.POINTER(PflowVarTransformC),
+                                        C.POINTER(SrpostPflowOut), vp, vp]
+    lib.srpost_last_error.restype = C.c_char_p
+    lib.srpost_last_error.argtypes = []
     _LIB = lib
     return lib
+
+
+def check_post(lib: C.CDLL, rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib.srpost_last_error()
+        raise RuntimeError(f"{what} failed (code {rc}): {msg.decode() if msg else '?'}")
 
 
 def check_pflow(lib: C.CDLL, handle, rc: int, what: str) -> None:

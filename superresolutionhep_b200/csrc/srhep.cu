@@ -1115,3 +1115,5 @@ int srhep_get_tap(SrhepHandle* h, const char* name, float* out, size_t n_floats,
 }  // extern "C"
 
 #include "pflow.inl"
+
+#include "post.inl"

@@ -45,6 +45,13 @@ def test_every_declared_pflow_symbol_is_exported(lib):
     assert set(names) == set(_lib.PFLOW_EXPORTS)
 
 
+def test_every_declared_post_symbol_is_exported(lib):
+    names = _declared_functions("srhep_post.h", "srpost_")
+    assert set(names) == set(_lib.POST_EXPORTS)
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/srhep_post.h but not exported"
+
+
 def test_pflow_weight_layout_matches_reference_checkpoint(lib, golden_dir):
     """The drop-in SAPF has the reference's state_dict keys, order and shapes (real pf_hr checkpoint)."""
     from superresolutionhep_b200.default_configs import pflow_config, pflow_var_transform
