@@ -211,7 +211,7 @@ def _main():
     ap.add_argument("--workload", default="single_e", choices=["single_e", "multipart"])
     ap.add_argument("--events", type=int, default=4096, help="events per GPU per step")
     ap.add_argument("--n-steps", type=int, default=25)
-    ap.add_argument("--precision", default=os.environ.get("SRHEP_BENCH_PRECISION", "bf16"), choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default=os.environ.get("SRHEP_BENCH_PRECISION", "bf16"), choices=["bf16", "fp16", "fp32"])
     ap.add_argument("--ref-events", type=int, default=64, help="events per step of the CPU reference arm / cpu_baseline sample")
     ap.add_argument("--pass-tokens", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -222,7 +222,7 @@ def _main():
         run_reference(args)
         return
     if args.steps is None:
-        args.steps = 5 if args.precision == "bf16" else 3
+        args.steps = 3 if args.precision == "fp32" else 5
 
     import torch.distributed as dist
     from superresolutionhep_b200 import FlowModel, _lib
@@ -367,7 +367,7 @@ def _main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32"}[args.precision], "data": "synthetic",
             "config": workload_config(args, B, args.precision),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,

@@ -45,6 +45,7 @@ def rel_l2(a, b):
 @pytest.mark.parametrize("kind,counts", [
     ("single_e", [4, 128, 132, 36, 260, 500]),
     ("multipart", [16, 0, 304, 48, 1600, 3280, 16]),        # multi-tile attention, empty event, max length
+    ("single_e", [4] * 40 + [8] * 30 + [132, 4, 4, 260]),   # > 16 events inside one 128-row tile: the chain kernel's unstaged adaLN path
 ])
 def test_velocity_matches_oracle(precision, kind, counts):
     m, sd, dims = make_model(kind, 21, precision)
