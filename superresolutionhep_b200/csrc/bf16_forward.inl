@@ -192,10 +192,10 @@ void launch_attn_bf16(Engine& E, const Pass& p, __nv_bfloat16* out) {
     q.dbg = nullptr;
     static long long* adbg = nullptr;
     static int adbg_calls = 0;
-    const bool dbg = getenv("SRHEP_ATTN_DBG") && (++adbg_calls == 8);
+    const bool dbg = h->sw.attn_dbg && (++adbg_calls == 8);
     if (dbg) { if (!adbg) cudaMalloc(&adbg, 256 * sizeof(long long)); cudaMemsetAsync(adbg, 0, 256 * sizeof(long long), E.s); q.dbg = adbg; }
     dim3 grid(std::max(1, std::min(q.n_items, 2 * 148 / d.heads)), d.heads);
-    if (!getenv("SRHEP_ATTN_V1")) {
+    if (!h->sw.attn_v1) {
         if (q.fp16) attn2_bf16_kernel<true><<<grid, kAtt2Threads, kAtt2SmemBytes, E.s>>>(h->bw.tm_qkv, h->bw.tm_kv64, q);
         else attn2_bf16_kernel<false><<<grid, kAtt2Threads, kAtt2SmemBytes, E.s>>>(h->bw.tm_qkv, h->bw.tm_kv64, q);
     }
@@ -243,7 +243,7 @@ void launch_chain(Engine& E, int M, int l, const int* rev) {
     const int m_tiles = (M + 127) / 128;
     const int grid = std::max(1, std::min(m_tiles, 2 * 148));
     static long long* dbg_dev = nullptr;
-    const bool dbg = getenv("SRHEP_CHAIN_DBG") && l == 1;
+    const bool dbg = h->sw.chain_dbg && l == 1;
     if (dbg) { if (!dbg_dev) cudaMalloc(&dbg_dev, 256 * sizeof(long long)); cudaMemsetAsync(dbg_dev, 0, 256 * sizeof(long long), E.s); q.dbg = dbg_dev; }
     if (q.fp16) layer_chain_kernel<true><<<grid, kChainThreads, kChainSmemBytes, E.s>>>(bw.tm_b, q);
     else layer_chain_kernel<false><<<grid, kChainThreads, kChainSmemBytes, E.s>>>(bw.tm_b, q);
@@ -270,7 +270,7 @@ void bf16_forward(Engine& E, const Pass& p, const int* rev, const StageRef& st) 
     const int fp16 = h->precision == SRHEP_PREC_FP16;
     float* x = h->xres;
     const float* mod = h->mod;
-    const bool chain = (H == kChainH && d.mlp_hid == kChainH) && !getenv("SRHEP_NO_CHAIN");
+    const bool chain = (H == kChainH && d.mlp_hid == kChainH) && !h->sw.no_chain;
     E.x_blocked = chain;
     __nv_bfloat16* a = (__nv_bfloat16*)h->act_a; __nv_bfloat16* b = (__nv_bfloat16*)h->act_b;
     __nv_bfloat16* qkv = (__nv_bfloat16*)h->qkv_lp;
@@ -295,7 +295,7 @@ void bf16_forward(Engine& E, const Pass& p, const int* rev, const StageRef& st) 
           launch_gemm_bf16<256>(E, bw.tm_ln, M, H, 3 * H, bw.img + bw.qkv[0], qkv, 3 * H, 1, ep); }
         for (int l = 0; l < d.layers; ++l) {
             E.cat = SRHEP_CAT_ATTN;
-            if (!fp16 && getenv("SRHEP_ATTN_SIMT")) E.attention_simt<__nv_bfloat16>(p, qkv, b);
+            if (!fp16 && h->sw.attn_simt) E.attention_simt<__nv_bfloat16>(p, qkv, b);
             else launch_attn_bf16(E, p, b);
             E.cat = SRHEP_CAT_CHAIN;
             launch_chain(E, M, l, rev);
@@ -309,11 +309,11 @@ void bf16_forward(Engine& E, const Pass& p, const int* rev, const StageRef& st) 
         { GemmEpilogue ep; ep.bias = h->bqkv + (size_t)l * 3 * H;
           launch_gemm_bf16<256>(E, bw.tm_ln, M, H, 3 * H, bw.img + bw.qkv[l], qkv, 3 * H, 1, ep); }
         E.cat = SRHEP_CAT_ATTN;
-        if (!fp16 && getenv("SRHEP_ATTN_SIMT")) E.attention_simt<__nv_bfloat16>(p, qkv, b);
+        if (!fp16 && h->sw.attn_simt) E.attention_simt<__nv_bfloat16>(p, qkv, b);
         else launch_attn_bf16(E, p, b);
         E.cat = SRHEP_CAT_OUT;
         { GemmEpilogue ep; ep.bias = bl; ep.gate = ml + 2 * H; ep.ld_gate = h->mod_width; ep.row_event = rev; ep.resid = x; ep.ld_resid = H;
-          if (getenv("SRHEP_NO_LNFUSE")) {
+          if (h->sw.no_lnfuse) {
               launch_gemm_bf16<256>(E, bw.tm_b, M, H, H, bw.img + bw.out[l], x, H, 0, ep);
               const Layout::Layer& y = L.layers[l];
               E.cat = SRHEP_CAT_LN;
@@ -332,7 +332,7 @@ void bf16_forward(Engine& E, const Pass& p, const int* rev, const StageRef& st) 
     }
     E.cat = SRHEP_CAT_HEAD;
     const int hw = d.v_in + d.ctx;
-    if (getenv("SRHEP_HEAD_FP32")) {
+    if (h->sw.head_fp32) {
         E.head_prep<float>(E.head_params(p, x), (float*)h->act_a, hw);
         GemmEpilogue ep; ep.bias = E.W(L.h1.b); ep.act = 1;
         E.gemm_f32<float>((float*)h->act_a, hw, E.W(L.h1.w), hw, h->h1buf, d.head_h1, M, d.head_h1, hw, ep);
@@ -340,7 +340,7 @@ void bf16_forward(Engine& E, const Pass& p, const int* rev, const StageRef& st) 
     if (fp16) E.head_prep<__half>(E.head_params(p, x), (__half*)a, hw);
     else E.head_prep<__nv_bfloat16>(E.head_params(p, x), a, hw);
     E.head_done = false;
-    if (bw.head_chain && !getenv("SRHEP_NO_HEADCHAIN")) {
+    if (bw.head_chain && !h->sw.no_headchain) {
         if (!E.rc) {
             HeadChainParams q;
             q.M = M; q.fp16 = fp16; q.final_ln = d.head_final_ln;

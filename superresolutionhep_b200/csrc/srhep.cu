@@ -108,6 +108,8 @@ struct SrhepHandle {
     Bf16Weights bw;                     // bf16 re-packed GEMM operands (SRHEP_PREC_BF16)
     int mod_width = 0;
 
+    // diagnostic switches (environment, read once per API call: A/B comparisons in the tests and tools)
+    struct Switches { bool no_chain = false, attn_simt = false, attn_v1 = false, no_lnfuse = false, head_fp32 = false, no_headchain = false, chain_dbg = false, attn_dbg = false; } sw;
     // options
     int64_t pass_tokens = 0;
     int use_graph = 1;
@@ -185,6 +187,12 @@ int dev_alloc(SrhepHandle* h, T*& p, size_t n) {
 }
 
 bool is_lp(const SrhepHandle* h) { return h->precision != SRHEP_PREC_FP32; }
+void read_switches(SrhepHandle* h) {
+    auto on = [](const char* n) { const char* v = getenv(n); return v && *v && *v != '0'; };
+    h->sw.no_chain = on("SRHEP_NO_CHAIN"); h->sw.attn_simt = on("SRHEP_ATTN_SIMT"); h->sw.attn_v1 = on("SRHEP_ATTN_V1");
+    h->sw.no_lnfuse = on("SRHEP_NO_LNFUSE"); h->sw.head_fp32 = on("SRHEP_HEAD_FP32"); h->sw.no_headchain = on("SRHEP_NO_HEADCHAIN");
+    h->sw.chain_dbg = on("SRHEP_CHAIN_DBG"); h->sw.attn_dbg = on("SRHEP_ATTN_DBG");
+}
 size_t act_elem_size(const SrhepHandle* h) { return is_lp(h) ? 2 : 4; }
 
 int validate_dims(const SrhepDims& d) {
@@ -739,6 +747,7 @@ int srhep_bind_events(SrhepHandle* h, const SrhepCond* c, const int32_t* cu, int
     cudaStream_t s = (cudaStream_t)stream;
     CK(h, cudaStreamSynchronize(s));          // previous work may still read the maps rebuilt below
     drop_graphs(h);
+    read_switches(h);
     h->bound = false; h->cond = *c; h->B = B; h->T = T;
     h->cu_host.assign(cu, cu + B + 1);
 
@@ -810,6 +819,7 @@ int srhep_bind_events(SrhepHandle* h, const SrhepCond* c, const int32_t* cu, int
 
 int srhep_velocity(SrhepHandle* h, const float* x, const float* t, float* v, void* stream) {
     if (!h) return SRHEP_E_INVALID;
+    read_switches(h);
     if (!h->bound) return fail(h, SRHEP_E_STATE, "srhep_bind_events must be called first");
     if (h->B == 0) return SRHEP_OK;
     if (!t || (h->T > 0 && (!x || !v))) return fail(h, SRHEP_E_INVALID, "null argument");
@@ -820,6 +830,7 @@ int srhep_velocity(SrhepHandle* h, const float* x, const float* t, float* v, voi
 int srhep_sample(SrhepHandle* h, const float* x0, const float* tg, int32_t n_steps, int32_t method, int32_t ret_seq,
                  float* x_seq, int32_t* nfe_out, void* stream) {
     if (!h) return SRHEP_E_INVALID;
+    read_switches(h);
     if (!h->bound) return fail(h, SRHEP_E_STATE, "srhep_bind_events must be called first");
     if (n_steps < 1 || !tg) return fail(h, SRHEP_E_INVALID, "n_steps >= 1 and a time grid are required");
     if (method != SRHEP_EULER && method != SRHEP_MIDPOINT && method != SRHEP_RK4)
@@ -922,6 +933,7 @@ int srhep_sample(SrhepHandle* h, const float* x0, const float* tg, int32_t n_ste
 int srhep_sample_dopri5(SrhepHandle* h, const float* x0, const float* tg, int32_t n_steps, float atol, float rtol,
                         int32_t ret_seq, float* x_seq, int32_t* stats_out, void* stream) {
     if (!h) return SRHEP_E_INVALID;
+    read_switches(h);
     if (!h->bound) return fail(h, SRHEP_E_STATE, "srhep_bind_events must be called first");
     if (n_steps < 1 || !tg) return fail(h, SRHEP_E_INVALID, "n_steps >= 1 and a time grid are required");
     if (!(atol > 0.f) || !(rtol >= 0.f)) return fail(h, SRHEP_E_INVALID, "atol > 0 and rtol >= 0 required");
@@ -1062,6 +1074,7 @@ int srhep_sample_dopri5(SrhepHandle* h, const float* x0, const float* tg, int32_
 
 int srhep_profile(SrhepHandle* h, const float* x, float t, float* v, float* ms_by_cat, int32_t* launches_by_cat, void* stream) {
     if (!h) return SRHEP_E_INVALID;
+    read_switches(h);
     if (!h->bound) return fail(h, SRHEP_E_STATE, "srhep_bind_events must be called first");
     if (!ms_by_cat || !launches_by_cat || (h->T > 0 && (!x || !v))) return fail(h, SRHEP_E_INVALID, "null argument");
     for (int i = 0; i < SRHEP_NCAT; ++i) { ms_by_cat[i] = 0.f; launches_by_cat[i] = 0; }
