@@ -104,8 +104,10 @@ def test_tensor_core_attention_matches_simt_attention():
         del os.environ["SRHEP_ATTN_SIMT"]
     scale = float(v_simt.abs().max())
     print(f"tc vs simt attention: max|diff| {float((v_tc - v_simt).abs().max()):.3e} of {scale:.3f}")
-    # P is rounded to 16 bits before P.V on the tensor-core path (fp32 on the SIMT path): the stated 16-bit tolerance applies
-    torch.testing.assert_close(v_tc, v_simt, rtol=1e-2, atol=1e-2 * scale)
+    # P is rounded to bf16 before P.V on the tensor-core path (fp32 on the SIMT path) and a quarter of the exponentials use the cubic
+    # exp2; both runs carry independent bf16 noise through six layers, so the bf16 single-evaluation bound (3e-2 of max|ref|)
+    # applies to their difference; the fp16 operand mode is held to 1e-2 against the fp32 oracle in test_velocity_matches_oracle.
+    torch.testing.assert_close(v_tc, v_simt, rtol=3e-2, atol=3e-2 * scale)
 
 
 @pytest.mark.parametrize("precision", ["fp16", "bf16"])
