@@ -17,14 +17,14 @@ EncodeTiledFn get_encode_fn() {
 }
 
 // bf16 row-major [rows, cols] with row pitch ld (elements); box = 64 columns x 128 rows, 128B swizzle
-int make_a_tmap(SrhepHandle* h, CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows = kGemmBM) {
+int make_a_tmap(SrhepHandle* h, CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows = kGemmBM, int force_fp16 = 0) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return fail(h, SRHEP_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t dims[2] = {cols, rows};
     cuuint64_t strides[1] = {ld * 2};
     cuuint32_t box[2] = {(cuuint32_t)kGemmBK, (cuuint32_t)box_rows};
     cuuint32_t es[2] = {1, 1};
-    CUresult r = enc(m, (h->precision == SRHEP_PREC_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = enc(m, ((h->precision == SRHEP_PREC_FP16 || force_fp16) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(h, SRHEP_E_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu", (int)r,
                                        (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld);
@@ -86,10 +86,13 @@ int bf16_pack_weights(SrhepHandle* h, const float* wh) {
         pack_weight(img, bw.mlp1[l], wh + y.m1.w, H, H, H, H, 256, fp16);
         pack_weight(img, bw.mlp2[l], wh + y.m2.w, H, H, H, H, 256, fp16);
     }
-    pack_weight(img, bw.head1, wh + L.h1.w, hk, d.head_h1, hk, hk, 128, fp16);
+    // The velocity head ends in a 32-term dot product with cancellation: its operand rounding dominates the error of v (bf16 operands: rel-L2 2e-2
+    // on v for 3e-3 on the transformer output).  Every head operand is a LayerNorm output or a weight, far inside fp16 range, so the fused
+    // head runs on fp16 operands (8x finer mantissa, same tcgen05 rate) whatever the operand format of the transformer is.
+    pack_weight(img, bw.head1, wh + L.h1.w, hk, d.head_h1, hk, hk, 128, fp16 || bw.head_chain);
     if (bw.head_chain) {
-        pack_weight(img, bw.head2, wh + L.h2.w, kHeadH1, kHeadH2, kHeadH1, kHeadH1, kHeadH2, fp16);
-        pack_weight(img, bw.head3, wh + L.h3.w, kHeadH2, kHeadH3, kHeadH2, kHeadH2, kHeadH3, fp16);
+        pack_weight(img, bw.head2, wh + L.h2.w, kHeadH1, kHeadH2, kHeadH1, kHeadH1, kHeadH2, true);
+        pack_weight(img, bw.head3, wh + L.h3.w, kHeadH2, kHeadH3, kHeadH2, kHeadH2, kHeadH3, true);
         memcpy(bw.head_b1, wh + L.h1.b, sizeof bw.head_b1); memcpy(bw.head_b2, wh + L.h2.b, sizeof bw.head_b2);
         memcpy(bw.head_b3, wh + L.h3.b, sizeof bw.head_b3); memcpy(bw.head_w4, wh + L.h4.w, sizeof bw.head_w4);
         bw.head_b4 = wh[L.h4.b];
@@ -154,7 +157,7 @@ int bf16_on_bind(SrhepHandle* h) {
     CK(h, cudaMemset(bw.tok_lp, 0, R * bw.feat0_kpad * 2));      // the K padding columns stay zero; the embedding kernel writes the rest
     int rc;
     if ((rc = make_a_tmap(h, &bw.tm_ln, h->act_a, R, d.h_dim, d.h_dim))) return rc;
-    if ((rc = make_a_tmap(h, &bw.tm_hin, h->act_a, R, d.v_in + d.ctx, d.v_in + d.ctx))) return rc;
+    if ((rc = make_a_tmap(h, &bw.tm_hin, h->act_a, R, d.v_in + d.ctx, d.v_in + d.ctx, kGemmBM, bw.head_chain ? 1 : 0))) return rc;      // the fused head always runs on fp16 operands
     if ((rc = make_a_tmap(h, &bw.tm_b, h->act_b, R, d.h_dim, d.h_dim))) return rc;
     if ((rc = make_a_tmap(h, &bw.tm_tok, bw.tok_lp, R, bw.feat0_kpad, bw.feat0_kpad))) return rc;
     if ((rc = make_a_tmap(h, &bw.tm_qkv, h->qkv_lp, R, 3 * d.h_dim, 3 * d.h_dim))) return rc;
@@ -337,13 +340,14 @@ void bf16_forward(Engine& E, const Pass& p, const int* rev, const StageRef& st) 
         GemmEpilogue ep; ep.bias = E.W(L.h1.b); ep.act = 1;
         E.gemm_f32<float>((float*)h->act_a, hw, E.W(L.h1.w), hw, h->h1buf, d.head_h1, M, d.head_h1, hw, ep);
     } else {
-    if (fp16) E.head_prep<__half>(E.head_params(p, x), (__half*)a, hw);
+    const bool fused_head = bw.head_chain && !h->sw.no_headchain;
+    if (fp16 || fused_head) E.head_prep<__half>(E.head_params(p, x), (__half*)a, hw);
     else E.head_prep<__nv_bfloat16>(E.head_params(p, x), a, hw);
     E.head_done = false;
-    if (bw.head_chain && !h->sw.no_headchain) {
+    if (fused_head) {
         if (!E.rc) {
             HeadChainParams q;
-            q.M = M; q.fp16 = fp16; q.final_ln = d.head_final_ln;
+            q.M = M; q.fp16 = 1; q.final_ln = d.head_final_ln;
             q.w1 = bw.img + bw.head1; q.w2 = bw.img + bw.head2; q.w3 = bw.img + bw.head3;
             memcpy(q.b1, bw.head_b1, sizeof q.b1); memcpy(q.b2, bw.head_b2, sizeof q.b2); memcpy(q.b3, bw.head_b3, sizeof q.b3);
             memcpy(q.w4, bw.head_w4, sizeof q.w4); q.b4 = bw.head_b4;
