@@ -75,6 +75,9 @@ int bf16_pack_weights(SrhepHandle* h, const float* wh) {
     bw.head1 = take(d.head_h1, hk);
     bw.head_chain = hk == kHeadK1 && d.head_h1 == kHeadH1 && d.head_h2 == kHeadH2 && d.head_h3 == kHeadH3;
     if (bw.head_chain) { bw.head2 = take(kHeadH2, kHeadH1); bw.head3 = take(kHeadH3, kHeadH2); }
+    bw.embed_tc = d.etaphi_in == 3 && d.etaphi_hid == 64 && d.proxy_hid == 64 && d.noisy_hid == 64 && d.etaphi_out == 32 && d.proxy_out == 31 &&
+                  d.noisy_out == 64 && d.layer_out == 32 && d.t_emb == 64 && d.cond == 96;
+    if (bw.embed_tc) bw.embed_w = take(128, 64);
     std::vector<uint8_t> img(off);
     const bool fp16 = h->precision == SRHEP_PREC_FP16;
     pack_weight(img, bw.feat0, wh + L.feat0.w, L.feat0.in, H, ncol, bw.feat0_kpad, 256, fp16);
@@ -96,6 +99,33 @@ int bf16_pack_weights(SrhepHandle* h, const float* wh) {
         memcpy(bw.head_b1, wh + L.h1.b, sizeof bw.head_b1); memcpy(bw.head_b2, wh + L.h2.b, sizeof bw.head_b2);
         memcpy(bw.head_b3, wh + L.h3.b, sizeof bw.head_b3); memcpy(bw.head_w4, wh + L.h4.w, sizeof bw.head_w4);
         bw.head_b4 = wh[L.h4.b];
+    }
+    if (bw.embed_tc) {
+        // block-diagonal second Linear of the three per-cell nets: GEMM column g <- its own net's 64 hidden units (column 63 = padding)
+        std::vector<float> w2((size_t)128 * 64, 0.f);
+        for (int o = 0; o < 32; ++o) memcpy(&w2[(size_t)o * 64], wh + L.eta3.w + (size_t)o * 64, 64 * sizeof(float));
+        for (int o = 0; o < 31; ++o) memcpy(&w2[(size_t)(32 + o) * 64], wh + L.prx3.w + (size_t)o * 64, 64 * sizeof(float));
+        for (int o = 0; o < 64; ++o) memcpy(&w2[(size_t)(64 + o) * 64], wh + L.nsy3.w + (size_t)o * 64, 64 * sizeof(float));
+        pack_weight(img, bw.embed_w, w2.data(), 64, 128, 64, 64, 128, true);
+        EmbedTcParams* q = new (std::nothrow) EmbedTcParams();
+        if (!q) return fail(h, SRHEP_E_NOMEM, "host allocation failed");
+        memset(q, 0, sizeof *q);
+        const Lin* l1[3] = {&L.eta1, &L.prx1, &L.nsy1};
+        const int dd[3] = {3, 1, 1};
+        for (int n = 0; n < 3; ++n)
+            for (int j = 0; j < 64; ++j) {
+                const float* row = wh + l1[n]->w + (size_t)j * l1[n]->in;
+                double sacc = 0;
+                for (int k = dd[n]; k < l1[n]->in; ++k) sacc += row[k];
+                q->r1[n * 64 + j] = (float)sacc; q->b1[n * 64 + j] = wh[l1[n]->b + j]; q->w0[n * 64 + j] = row[0];
+                if (n == 0) { q->w1[j] = row[1]; q->w2[j] = row[2]; }
+            }
+        for (int o = 0; o < 32; ++o) q->b2[o] = wh[L.eta3.b + o];
+        for (int o = 0; o < 31; ++o) q->b2[32 + o] = wh[L.prx3.b + o];
+        for (int o = 0; o < 64; ++o) q->b2[64 + o] = wh[L.nsy3.b + o];
+        q->te = (float)d.t_emb;
+        bw.embed_tpl = q;
+        CK(h, cudaFuncSetAttribute(embed_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmbSmemBytes));
     }
     CK(h, cudaMalloc(&bw.img, img.size()));
     CK(h, cudaMemcpy(bw.img, img.data(), img.size(), cudaMemcpyHostToDevice));
@@ -145,6 +175,7 @@ void bf16_free_weights(SrhepHandle* h) {
     if (h->bw.bias) cudaFree(h->bw.bias);
     if (h->bw.tok_lp) cudaFree(h->bw.tok_lp);
     free(h->bw.bias_h); free(h->bw.bqkv_h);
+    delete static_cast<EmbedTcParams*>(h->bw.embed_tpl);
     h->bw = Bf16Weights();
 }
 

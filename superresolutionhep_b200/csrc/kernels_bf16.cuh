@@ -930,6 +930,9 @@ struct Bf16Weights {
     // offsets (bytes) into img
     size_t feat0 = 0, head1 = 0, head2 = 0, head3 = 0;
     bool head_chain = false;         // fused tcgen05 head available (kernels_head.cuh)
+    bool embed_tc = false;           // tensor-core embedding available (kernels_embed.cuh)
+    size_t embed_w = 0;              // its block-diagonal second-layer weight image
+    void* embed_tpl = nullptr;       // host-side EmbedTcParams with the constants filled in
     float head_b1[128], head_b2[64], head_b3[32], head_w4[32], head_b4;
     size_t qkv[64] = {0}, out[64] = {0}, mlp1[64] = {0}, mlp2[64] = {0};
     float* bias = nullptr;           // 16-byte aligned copies: per layer [out | mlp1 | mlp2], then head1

@@ -21,6 +21,7 @@
 #include "kernels_chain.cuh"
 #include "kernels_head.cuh"
 #include "kernels_attn.cuh"
+#include "kernels_embed.cuh"
 
 using namespace srhep;
 
@@ -109,7 +110,7 @@ struct SrhepHandle {
     int mod_width = 0;
 
     // diagnostic switches (environment, read once per API call: A/B comparisons in the tests and tools)
-    struct Switches { bool no_chain = false, attn_simt = false, attn_v1 = false, no_lnfuse = false, head_fp32 = false, no_headchain = false, chain_dbg = false, attn_dbg = false; } sw;
+    struct Switches { bool no_chain = false, attn_simt = false, attn_v1 = false, no_lnfuse = false, head_fp32 = false, no_headchain = false, no_embed_tc = false, chain_dbg = false, attn_dbg = false; } sw;
     // options
     int64_t pass_tokens = 0;
     int use_graph = 1;
@@ -190,7 +191,7 @@ bool is_lp(const SrhepHandle* h) { return h->precision != SRHEP_PREC_FP32; }
 void read_switches(SrhepHandle* h) {
     auto on = [](const char* n) { const char* v = getenv(n); return v && *v && *v != '0'; };
     h->sw.no_chain = on("SRHEP_NO_CHAIN"); h->sw.attn_simt = on("SRHEP_ATTN_SIMT"); h->sw.attn_v1 = on("SRHEP_ATTN_V1");
-    h->sw.no_lnfuse = on("SRHEP_NO_LNFUSE"); h->sw.head_fp32 = on("SRHEP_HEAD_FP32"); h->sw.no_headchain = on("SRHEP_NO_HEADCHAIN");
+    h->sw.no_lnfuse = on("SRHEP_NO_LNFUSE"); h->sw.head_fp32 = on("SRHEP_HEAD_FP32"); h->sw.no_headchain = on("SRHEP_NO_HEADCHAIN"); h->sw.no_embed_tc = on("SRHEP_NO_EMBED_TC");
     h->sw.chain_dbg = on("SRHEP_CHAIN_DBG"); h->sw.attn_dbg = on("SRHEP_ATTN_DBG");
 }
 size_t act_elem_size(const SrhepHandle* h) { return is_lp(h) ? 2 : 4; }
@@ -334,7 +335,17 @@ struct Engine {
             q.stage = st; q.e0 = p.e0;
             if (!rc) { event_prep_kernel<<<nE, 128, 0, s>>>(q); check("event_prep"); }
         }
-        if (M > 0) {   // 2. per-cell embeddings + chunk sums
+        const bool embed_tc = lp && h->bw.embed_tc && !h->sw.no_embed_tc;
+        if (M > 0 && embed_tc) {   // 2. per-cell embeddings on the tensor core (kernels_embed.cuh)
+            EmbedTcParams q = *static_cast<const EmbedTcParams*>(h->bw.embed_tpl);
+            q.M = M; q.row0 = p.r0; q.lp_fp16 = h->precision == SRHEP_PREC_FP16;
+            q.eta = h->cond.eta; q.cosphi = h->cond.cosphi; q.sinphi = h->cond.sinphi; q.e_proxy = h->cond.e_proxy; q.layer = h->cond.layer;
+            q.stage = st; q.row_event = rev;
+            q.ev_a = h->ev_a; q.ev_stats = h->ev_stats; q.layer_out = h->layer_out;
+            q.w_img = h->bw.img + h->bw.embed_w;
+            q.tok_feat = h->tok_feat; q.ld = ncol; q.tok_lp = h->bw.tok_lp; q.ld_lp = h->bw.feat0_kpad;
+            if (!rc) { embed_tc_kernel<<<std::min((M + 127) / 128, 3 * 148), kEmbThreads, kEmbSmemBytes, s>>>(q); check("embed_tc"); }
+        } else if (M > 0) {   // 2. per-cell embeddings + chunk sums
             EmbedTokParams q;
             q.etaphi = net(L.eta1, L.eta3, d.etaphi_in, 0);
             q.proxy = net(L.prx1, L.prx3, 1, 2);
@@ -348,6 +359,12 @@ struct Engine {
             q.tok_lp = lp ? (void*)h->bw.tok_lp : nullptr; q.ld_lp = h->bw.feat0_kpad; q.lp_fp16 = h->precision == SRHEP_PREC_FP16;
             if (!rc) { embed_tokens_kernel<<<std::min(p.c1 - p.c0, 148 * 8), 192, 0, s>>>(q); check("embed_tokens"); }
         }
+        if (embed_tc) {   // 3. context from the cond columns of tok_feat
+            ContextRowsParams q;
+            q.temb = h->temb; q.tok_feat = h->tok_feat; q.ld = ncol; q.row0 = p.r0; q.cu_seqlens = h->cu_dev;
+            q.ctx = h->ctx; q.silu_ctx = h->silu_ctx; q.t_emb = d.t_emb; q.cond = d.cond; q.e0 = p.e0;
+            if (!rc) { context_rows_kernel<<<nE, 384, 0, s>>>(q); check("context_rows"); }
+        } else
         {   // 3. context
             ContextParams q;
             q.temb = h->temb; q.partial = h->partial; q.ev_chunk_start = h->ev_chunk_start; q.cu_seqlens = h->cu_dev;
