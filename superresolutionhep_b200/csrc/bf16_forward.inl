@@ -132,7 +132,8 @@ int bf16_pack_weights(SrhepHandle* h, const float* wh) {
     bw.bytes = img.size();
     bw.bias_layer_stride = 7 * (size_t)H;      // out.b | mlp1.b | mlp2.b | norm1.w | norm1.b | norm2.w | norm2.b
     bw.bias_head1 = bw.bias_layer_stride * d.layers;
-    std::vector<float> b(bw.bias_head1 + d.head_h1);
+    bw.bias_fn = bw.bias_head1 + d.head_h1;
+    std::vector<float> b(bw.bias_fn + 2 * (size_t)H + 2 * (size_t)d.v_in);
     for (int l = 0; l < d.layers; ++l) {
         const Layout::Layer& y = L.layers[l];
         memcpy(&b[l * bw.bias_layer_stride], wh + y.o.b, H * sizeof(float));
@@ -144,6 +145,8 @@ int bf16_pack_weights(SrhepHandle* h, const float* wh) {
         memcpy(&b[l * bw.bias_layer_stride + 6 * H], wh + y.n2b, H * sizeof(float));
     }
     memcpy(&b[bw.bias_head1], wh + L.h1.b, d.head_h1 * sizeof(float));
+    memcpy(&b[bw.bias_fn], wh + L.fn_w, H * sizeof(float)); memcpy(&b[bw.bias_fn + H], wh + L.fn_b, H * sizeof(float));
+    memcpy(&b[bw.bias_fn + 2 * H], wh + L.nv_w, d.v_in * sizeof(float)); memcpy(&b[bw.bias_fn + 2 * H + d.v_in], wh + L.nv_b, d.v_in * sizeof(float));
     CK(h, cudaMalloc(&bw.bias, b.size() * sizeof(float)));
     CK(h, cudaMemcpy(bw.bias, b.data(), b.size() * sizeof(float), cudaMemcpyHostToDevice));
     bw.bias_h = (float*)malloc(b.size() * sizeof(float));

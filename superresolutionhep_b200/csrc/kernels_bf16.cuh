@@ -938,7 +938,7 @@ struct Bf16Weights {
     float* bias = nullptr;           // 16-byte aligned copies: per layer [out | mlp1 | mlp2], then head1
     float* bias_h = nullptr;         // host mirror of `bias` (per-column constants travel by value into the chain kernel)
     float* bqkv_h = nullptr;         // host mirror of the stacked q|k|v biases
-    size_t bias_layer_stride = 0, bias_head1 = 0;
+    size_t bias_layer_stride = 0, bias_head1 = 0, bias_fn = 0;     // bias_fn: final_norm w | b | norm_v_t w | b (16-byte aligned copies)
     __nv_bfloat16* tok_lp = nullptr; // [rows, feat0 K padded] bf16 copy of tok_feat (feat_0 GEMM A operand)
     int feat0_kpad = 0;
     CUtensorMap tm_ln, tm_hin, tm_b, tm_tok;      // A-operand maps over the pass workspace

@@ -7,6 +7,7 @@
 // Every kernel works on PACKED rows (real cells only); events are addressed through
 // cu_seqlens-derived maps, never through padding masks (SURVEY §7 "skip instead of mask").
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 
 namespace srhep {
@@ -629,6 +630,58 @@ __global__ void __launch_bounds__(256) head_prep_kernel(HeadPrepParams p, OutT* 
         else col = vin + lane + 32 * (j - PV);
         store_out(hin + (size_t)row * ldh + col, (v[j] - mean) * rstd);
     }
+}
+
+// float4 variant for the shipped dimensions (h = 256, cond = 96, ctx = 160) on the blocked residual layout: same mapping
+// (one warp per row, 8 rows per block) but every lane owns groups of 4 consecutive columns, so a row costs ~25 128-bit
+// memory instructions per lane instead of ~90 scalar ones (the scalar kernel is issue-bound: 64 % issue slots, 60 % LSU).
+// Pieces: h -> 2 per lane (cols 4 lane + 128 j); cond -> 1 (lanes 0-23); ctx -> 1 + 1 (lanes 0-7).  All row pointers 16-byte aligned.
+template <typename OutT>
+__global__ void __launch_bounds__(256) head_prep_v4_kernel(HeadPrepParams p, OutT* hin, int ldh) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= p.M) return;
+    const int ev = p.row_event[row];
+    const bool hc = lane < 24, hx1 = lane < 8;
+    auto ld4 = [](const float* q) { return *reinterpret_cast<const float4*>(q); };
+    auto st4 = [](OutT* q, float4 v) {
+        uint2 w;
+        if (std::is_same<OutT, __half>::value) { __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w); w.x = *reinterpret_cast<uint32_t*>(&a); w.y = *reinterpret_cast<uint32_t*>(&b); }
+        else { __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w); w.x = *reinterpret_cast<uint32_t*>(&a); w.y = *reinterpret_cast<uint32_t*>(&b); }
+        *reinterpret_cast<uint2*>(q) = w;
+    };
+    auto sum4 = [](float4 v) { return (v.x + v.y) + (v.z + v.w); };
+    auto sq4 = [](float4 v, float m) { const float a = v.x - m, b = v.y - m, c = v.z - m, d = v.w - m; return (a * a + b * b) + (c * c + d * d); };
+    auto aff4 = [](float4 v, float m, float r, float4 w, float4 b) { return make_float4(fmaf((v.x - m) * r, w.x, b.x), fmaf((v.y - m) * r, w.y, b.y), fmaf((v.z - m) * r, w.z, b.z), fmaf((v.w - m) * r, w.w, b.w)); };
+    auto mod4 = [](float4 v, float4 sc, float4 sh) { return make_float4(fmaf(v.x, 1.f + sc.x, sh.x), fmaf(v.y, 1.f + sc.y, sh.y), fmaf(v.z, 1.f + sc.z, sh.z), fmaf(v.w, 1.f + sc.w, sh.w)); };
+    auto nrm4 = [](float4 v, float m, float r) { return make_float4((v.x - m) * r, (v.y - m) * r, (v.z - m) * r, (v.w - m) * r); };
+    const int c0 = lane * 4, c1 = 128 + lane * 4;
+    float4 a0 = ld4(p.x + xblk_index(row, c0)), a1 = ld4(p.x + xblk_index(row, c1));
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 cc = hc ? ld4(p.tok_feat + (size_t)row * p.ldt + c0) : z4;
+    const float* cx = p.ctx + (size_t)ev * 160;
+    float4 x0 = ld4(cx + c0), x1 = hx1 ? ld4(cx + c1) : z4;
+    const float* sh = p.shift + (size_t)ev * p.ld_mod; const float* sc = p.scale + (size_t)ev * p.ld_mod;
+    // final_norm over h = 256
+    float mean = warp_sum(sum4(a0) + sum4(a1)) * (1.0f / 256.f);
+    float rstd = 1.0f / sqrtf(warp_sum(sq4(a0, mean) + sq4(a1, mean)) * (1.0f / 256.f) + kLnEps);
+    a0 = aff4(a0, mean, rstd, ld4(p.fn_w + c0), ld4(p.fn_b + c0));
+    a1 = aff4(a1, mean, rstd, ld4(p.fn_w + c1), ld4(p.fn_b + c1));
+    if (p.final_tap) { *reinterpret_cast<float4*>(p.final_tap + (size_t)row * 256 + c0) = a0; *reinterpret_cast<float4*>(p.final_tap + (size_t)row * 256 + c1) = a1; }
+    // norm_v_t over h + cond = 352, affine, modulate
+    mean = warp_sum(sum4(a0) + sum4(a1) + sum4(cc)) * (1.0f / 352.f);
+    rstd = 1.0f / sqrtf(warp_sum(sq4(a0, mean) + sq4(a1, mean) + (hc ? sq4(cc, mean) : 0.f)) * (1.0f / 352.f) + kLnEps);
+    a0 = mod4(aff4(a0, mean, rstd, ld4(p.nv_w + c0), ld4(p.nv_b + c0)), ld4(sc + c0), ld4(sh + c0));
+    a1 = mod4(aff4(a1, mean, rstd, ld4(p.nv_w + c1), ld4(p.nv_b + c1)), ld4(sc + c1), ld4(sh + c1));
+    if (hc) cc = mod4(aff4(cc, mean, rstd, ld4(p.nv_w + 256 + c0), ld4(p.nv_b + 256 + c0)), ld4(sc + 256 + c0), ld4(sh + 256 + c0));
+    // LayerNorm (no affine) over v_in + ctx = 512
+    mean = warp_sum(sum4(a0) + sum4(a1) + sum4(cc) + sum4(x0) + sum4(x1)) * (1.0f / 512.f);
+    rstd = 1.0f / sqrtf(warp_sum(sq4(a0, mean) + sq4(a1, mean) + (hc ? sq4(cc, mean) : 0.f) + sq4(x0, mean) + (hx1 ? sq4(x1, mean) : 0.f)) * (1.0f / 512.f) + kLnEps);
+    OutT* o = hin + (size_t)row * ldh;
+    st4(o + c0, nrm4(a0, mean, rstd)); st4(o + c1, nrm4(a1, mean, rstd));
+    if (hc) st4(o + 256 + c0, nrm4(cc, mean, rstd));
+    st4(o + 352 + c0, nrm4(x0, mean, rstd));
+    if (hx1) st4(o + 352 + c1, nrm4(x1, mean, rstd));
 }
 
 // ------------------------------------------------------------------------------------

@@ -110,7 +110,7 @@ struct SrhepHandle {
     int mod_width = 0;
 
     // diagnostic switches (environment, read once per API call: A/B comparisons in the tests and tools)
-    struct Switches { bool no_chain = false, attn_simt = false, attn_v1 = false, no_lnfuse = false, head_fp32 = false, no_headchain = false, no_embed_tc = false, chain_dbg = false, attn_dbg = false; } sw;
+    struct Switches { bool no_chain = false, attn_simt = false, attn_v1 = false, no_lnfuse = false, head_fp32 = false, no_headchain = false, no_embed_tc = false, head_prep_scalar = false, chain_dbg = false, attn_dbg = false; } sw;
     // options
     int64_t pass_tokens = 0;
     int use_graph = 1;
@@ -191,7 +191,7 @@ bool is_lp(const SrhepHandle* h) { return h->precision != SRHEP_PREC_FP32; }
 void read_switches(SrhepHandle* h) {
     auto on = [](const char* n) { const char* v = getenv(n); return v && *v && *v != '0'; };
     h->sw.no_chain = on("SRHEP_NO_CHAIN"); h->sw.attn_simt = on("SRHEP_ATTN_SIMT"); h->sw.attn_v1 = on("SRHEP_ATTN_V1");
-    h->sw.no_lnfuse = on("SRHEP_NO_LNFUSE"); h->sw.head_fp32 = on("SRHEP_HEAD_FP32"); h->sw.no_headchain = on("SRHEP_NO_HEADCHAIN"); h->sw.no_embed_tc = on("SRHEP_NO_EMBED_TC");
+    h->sw.no_lnfuse = on("SRHEP_NO_LNFUSE"); h->sw.head_fp32 = on("SRHEP_HEAD_FP32"); h->sw.no_headchain = on("SRHEP_NO_HEADCHAIN"); h->sw.no_embed_tc = on("SRHEP_NO_EMBED_TC"); h->sw.head_prep_scalar = on("SRHEP_HEAD_PREP_SCALAR");
     h->sw.chain_dbg = on("SRHEP_CHAIN_DBG"); h->sw.attn_dbg = on("SRHEP_ATTN_DBG");
 }
 size_t act_elem_size(const SrhepHandle* h) { return is_lp(h) ? 2 : 4; }
@@ -305,6 +305,11 @@ struct Engine {
         const SrhepDims& d = h->d;
         const int grid = (q.M + 7) / 8;
         const int ph = d.h_dim / 32, pc = d.cond / 32, px = d.ctx / 32;
+        if (ph == 8 && pc == 3 && px == 5 && q.x_blocked && sizeof(OutT) == 2 && q.ldt % 4 == 0 && is_lp(h) && !h->sw.head_prep_scalar) {
+            head_prep_v4_kernel<OutT><<<grid, 256, 0, s>>>(q, hin, ldh);
+            check("head_prep_v4");
+            return;
+        }
         if (ph == 8 && pc == 3 && px == 5) head_prep_kernel<OutT, 8, 3, 5><<<grid, 256, 0, s>>>(q, hin, ldh);
         else if (ph == 2 && pc == 3 && px == 5) head_prep_kernel<OutT, 2, 3, 5><<<grid, 256, 0, s>>>(q, hin, ldh);
         else { rc = fail(h, SRHEP_E_INVALID, "head_prep: unsupported (h,cond,ctx)/32 = (%d,%d,%d)", ph, pc, px); return; }
@@ -441,6 +446,10 @@ struct Engine {
         HeadPrepParams q;
         q.x = x; q.ldx = d.h_dim; q.tok_feat = h->tok_feat; q.ldt = d.cond + d.noisy_out;
         q.fn_w = W(L.fn_w); q.fn_b = W(L.fn_b); q.nv_w = W(L.nv_w); q.nv_b = W(L.nv_b);
+        if (is_lp(h) && h->bw.bias) {          // 16-byte aligned copies for the float4 kernel
+            const float* bf = h->bw.bias + h->bw.bias_fn;
+            q.fn_w = bf; q.fn_b = bf + d.h_dim; q.nv_w = bf + 2 * d.h_dim; q.nv_b = bf + 2 * d.h_dim + d.v_in;
+        }
         const float* mv = h->mod + (size_t)d.layers * 6 * d.h_dim;
         q.shift = mv; q.scale = mv + d.v_in; q.ld_mod = h->mod_width;
         q.ctx = h->ctx; q.ctx_dim = d.ctx; q.row_event = h->row_event + p.r0;
