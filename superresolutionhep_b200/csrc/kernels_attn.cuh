@@ -35,6 +35,79 @@ constexpr size_t kAtt2SmemBytes = kAtt2OffBars + 256;                     // 2 C
 #define ATT_STAMP(item, k) do { } while (0)
 #endif
 
+
+// One key tile of one query row: scores (64, or 32 when the second half of a ragged tile is all padding) -> P = exp2(S c - m)
+// in the 16-bit A-operand layout, running sum and lazy running maximum.  kHalf2 = false writes zeros for the second half.
+template <bool kFp16, bool kHalf2>
+__device__ __forceinline__ void att2_softmax_tile(uint32_t t_s, uint64_t* s_empty_bar, int lane, int kv_valid, int j, float scale_log2, float& m_ref, float& l,
+                                                  float& corr, bool& rescale, uint8_t* prow, int row, uint64_t* pv_bar, uint32_t pv_par) {
+    constexpr int fp16 = kFp16 ? 1 : 0;
+    uint32_t r0[32], r1[kHalf2 ? 32 : 1];
+    tmem_ld32(t_s, r0);
+    if (kHalf2) tmem_ld32(t_s + 32, reinterpret_cast<uint32_t (&)[32]>(r1));
+    tmem_ld_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(s_empty_bar);                   // the scores live in registers now: S(it + 2) may be issued
+    if (kv_valid < kAtt2KvTile) {                              // ragged last tile of the event: keys past its end count as -inf
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            if (i >= kv_valid) r0[i] = 0xff800000u;
+            if (kHalf2 && 32 + i >= kv_valid) r1[i] = 0xff800000u;
+        }
+    }
+    float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};       // four independent chains
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (kHalf2) mx4[u] = fmaxf(mx4[u], fmaxf(__uint_as_float(r0[i + u]), __uint_as_float(r1[i + u])));
+            else mx4[u] = fmaxf(mx4[u], __uint_as_float(r0[i + u]));
+        }
+    }
+    const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * scale_log2;
+    if (mx > m_ref + 8.f) {                                    // first tile: m_ref = -inf
+        if (j > 0) { corr = fast_exp2(m_ref - mx); rescale = true; }
+        m_ref = mx;
+    }
+    uint32_t pk[32];
+    const uint64_t sc2 = pack_f32x2(scale_log2, scale_log2), nm2 = pack_f32x2(-m_ref, -m_ref);
+    uint64_t l2a = 0ull, l2b = 0ull;                            // two packed running sums = four independent chains
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {                          // exp2(-inf) = 0 takes care of the masked keys
+        const uint64_t t0 = ffma2(pack_f32x2(__uint_as_float(r0[i]), __uint_as_float(r0[i + 1])), sc2, nm2);
+        const uint64_t t1 = ffma2(pack_f32x2(__uint_as_float(r0[i + 2]), __uint_as_float(r0[i + 3])), sc2, nm2);
+        const float e0 = fast_exp2(f32x2_lo(t0)), e1 = fast_exp2(f32x2_hi(t0));
+        float e2, e3;
+        if (kPolyMask & (1 << ((i >> 2) & 7))) exp2_poly_x2(t1, e2, e3);     // part of the exponentials leave the SFU for the FMA pipe
+        else { e2 = fast_exp2(f32x2_lo(t1)); e3 = fast_exp2(f32x2_hi(t1)); }
+        l2a = fadd2(l2a, pack_f32x2(e0, e1)); l2b = fadd2(l2b, pack_f32x2(e2, e3));
+        pk[i >> 1] = pack16(e0, e1, fp16); pk[(i >> 1) + 1] = pack16(e2, e3, fp16);
+    }
+    if (kHalf2) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+            const uint64_t t0 = ffma2(pack_f32x2(__uint_as_float(r1[i]), __uint_as_float(r1[i + 1])), sc2, nm2);
+            const uint64_t t1 = ffma2(pack_f32x2(__uint_as_float(r1[i + 2]), __uint_as_float(r1[i + 3])), sc2, nm2);
+            const float e0 = fast_exp2(f32x2_lo(t0)), e1 = fast_exp2(f32x2_hi(t0));
+            float e2, e3;
+            if (kPolyMask & (1 << ((i >> 2) & 7))) exp2_poly_x2(t1, e2, e3);
+            else { e2 = fast_exp2(f32x2_lo(t1)); e3 = fast_exp2(f32x2_hi(t1)); }
+            l2a = fadd2(l2a, pack_f32x2(e0, e1)); l2b = fadd2(l2b, pack_f32x2(e2, e3));
+            pk[16 + (i >> 1)] = pack16(e0, e1, fp16); pk[17 + (i >> 1)] = pack16(e2, e3, fp16);
+        }
+    }
+    l = fmaf(l, corr, (f32x2_lo(l2a) + f32x2_hi(l2a)) + (f32x2_lo(l2b) + f32x2_hi(l2b)));
+    if (pv_bar) mbar_wait(pv_bar, pv_par);                      // the P buffer is free once PV of tile it - 2 retired
+#pragma unroll
+    for (int g = 0; g < (kHalf2 ? 8 : 4); ++g)
+        *reinterpret_cast<uint4*>(prow + ((g ^ (row & 7)) << 4)) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+    if (!kHalf2) {
+#pragma unroll
+        for (int g = 4; g < 8; ++g) *reinterpret_cast<uint4*>(prow + ((g ^ (row & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);   // exp2(-inf) = 0 in either 16-bit format
+    }
+}
+
 template <bool kFp16>
 __global__ void __launch_bounds__(kAtt2Threads, 2) attn2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                                                                      AttnBf16Params p) {
@@ -149,71 +222,35 @@ __global__ void __launch_bounds__(kAtt2Threads, 2) attn2_bf16_kernel(const __gri
             const AttnItem a = p.items[w];
             const int n_kv = (a.k_len + kAtt2KvTile - 1) / kAtt2KvTile;
             float m_ref = -INFINITY, l = 0.f;
+            // query rows past the event's end (the last 128-row tile of an event is ragged): a warp whose 32 rows are all padding
+            // keeps the barrier protocol going but does none of the arithmetic (15 % of the softmax work on single_e shapes)
+            const bool wact = q * 32 < a.q_len;
+            if (!wact) {
+                for (int j = 0; j < n_kv; ++j, ++it) {
+                    const uint32_t b = it & 1;
+                    mbar_wait(&s_full[b], (it >> 1) & 1);
+                    if (lane == 0) mbar_arrive(&s_empty[b]);
+                    // the p_full phase of tile it - 2 must be over before this warp arrives for tile it
+                    if (it >= 2) mbar_wait(&pv_done[b], ((it >> 1) - 1) & 1);
+                    if (lane == 0) mbar_arrive(&p_full[b]);
+                }
+                mbar_wait(&pv_done[(it - 1) & 1], ((it - 1) >> 1) & 1);
+                if (lane == 0) mbar_arrive(o_empty);
+                continue;
+            }
             for (int j = 0; j < n_kv; ++j, ++it) {
                 const uint32_t b = it & 1;
                 const int kv_valid = min(kAtt2KvTile, a.k_len - j * kAtt2KvTile);
+                const bool half2 = kv_valid > 32;                            // ragged last key tile with at most 32 keys: its second half is all padding
                 mbar_wait(&s_full[b], (it >> 1) & 1);
                 if (warp == 2 && lane == 0) ATT_STAMP(item_i, 32 + j);
                 tc_fence_after();
-                uint32_t r0[32], r1[32];
-                tmem_ld32(t_lane + b * 64, r0);
-                tmem_ld32(t_lane + b * 64 + 32, r1);
-                tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&s_empty[b]);                   // the scores live in registers now: S(it + 2) may be issued
-                if (kv_valid < kAtt2KvTile) {                              // ragged last tile of the event: keys past its end count as -inf
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        if (i >= kv_valid) r0[i] = 0xff800000u;
-                        if (32 + i >= kv_valid) r1[i] = 0xff800000u;
-                    }
-                }
-                float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};       // four independent chains
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) mx4[u] = fmaxf(mx4[u], fmaxf(__uint_as_float(r0[i + u]), __uint_as_float(r1[i + u])));
-                }
-                const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * p.scale_log2;
                 float corr = 1.f;
                 bool rescale = false;
-                if (mx > m_ref + 8.f) {                                    // first tile: m_ref = -inf
-                    if (j > 0) { corr = fast_exp2(m_ref - mx); rescale = true; }
-                    m_ref = mx;
-                }
-                uint32_t pk[32];
-                const uint64_t sc2 = pack_f32x2(p.scale_log2, p.scale_log2), nm2 = pack_f32x2(-m_ref, -m_ref);
-                uint64_t l2a = 0ull, l2b = 0ull;                            // two packed running sums = four independent chains
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {                          // exp2(-inf) = 0 takes care of the masked keys
-                    const uint64_t t0 = ffma2(pack_f32x2(__uint_as_float(r0[i]), __uint_as_float(r0[i + 1])), sc2, nm2);
-                    const uint64_t t1 = ffma2(pack_f32x2(__uint_as_float(r0[i + 2]), __uint_as_float(r0[i + 3])), sc2, nm2);
-                    const float e0 = fast_exp2(f32x2_lo(t0)), e1 = fast_exp2(f32x2_hi(t0));
-                    float e2, e3;
-                    if (kPolyMask & (1 << ((i >> 2) & 7))) exp2_poly_x2(t1, e2, e3);     // part of the exponentials leave the SFU for the FMA pipe
-                    else { e2 = fast_exp2(f32x2_lo(t1)); e3 = fast_exp2(f32x2_hi(t1)); }
-                    l2a = fadd2(l2a, pack_f32x2(e0, e1)); l2b = fadd2(l2b, pack_f32x2(e2, e3));
-                    pk[i >> 1] = pack16(e0, e1, fp16); pk[(i >> 1) + 1] = pack16(e2, e3, fp16);
-                }
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const uint64_t t0 = ffma2(pack_f32x2(__uint_as_float(r1[i]), __uint_as_float(r1[i + 1])), sc2, nm2);
-                    const uint64_t t1 = ffma2(pack_f32x2(__uint_as_float(r1[i + 2]), __uint_as_float(r1[i + 3])), sc2, nm2);
-                    const float e0 = fast_exp2(f32x2_lo(t0)), e1 = fast_exp2(f32x2_hi(t0));
-                    float e2, e3;
-                    if (kPolyMask & (1 << ((i >> 2) & 7))) exp2_poly_x2(t1, e2, e3);
-                    else { e2 = fast_exp2(f32x2_lo(t1)); e3 = fast_exp2(f32x2_hi(t1)); }
-                    l2a = fadd2(l2a, pack_f32x2(e0, e1)); l2b = fadd2(l2b, pack_f32x2(e2, e3));
-                    pk[16 + (i >> 1)] = pack16(e0, e1, fp16); pk[17 + (i >> 1)] = pack16(e2, e3, fp16);
-                }
-                l = fmaf(l, corr, (f32x2_lo(l2a) + f32x2_hi(l2a)) + (f32x2_lo(l2b) + f32x2_hi(l2b)));
-                // the P buffer is free once PV of tile it - 2 retired
-                if (it >= 2) mbar_wait(&pv_done[b], ((it >> 1) - 1) & 1);
-                uint8_t* prow = s_p + b * 16384 + row * 128;
-#pragma unroll
-                for (int g = 0; g < 8; ++g)
-                    *reinterpret_cast<uint4*>(prow + ((g ^ (row & 7)) << 4)) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+                // the P buffer is free once PV of tile it - 2 retired (waited for inside, right before the stores)
+                uint64_t* pv_bar = it >= 2 ? &pv_done[b] : nullptr; const uint32_t pv_par = ((it >> 1) - 1) & 1;
+                if (half2) att2_softmax_tile<kFp16, true>(t_lane + b * 64, &s_empty[b], lane, kv_valid, j, p.scale_log2, m_ref, l, corr, rescale, s_p + b * 16384 + row * 128, row, pv_bar, pv_par);
+                else att2_softmax_tile<kFp16, false>(t_lane + b * 64, &s_empty[b], lane, kv_valid, j, p.scale_log2, m_ref, l, corr, rescale, s_p + b * 16384 + row * 128, row, pv_bar, pv_par);
                 if (__any_sync(0xffffffffu, rescale)) {                    // rare: raise the reference maximum; O must be quiescent (PV of tile it - 1 retired)
                     mbar_wait(&pv_done[(it - 1) & 1], ((it - 1) >> 1) & 1);
                     tc_fence_after();
