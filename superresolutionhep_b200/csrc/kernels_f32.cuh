@@ -387,6 +387,90 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
     }
 }
 
+// Larger-tile variant for the per-event contractions that are big enough to matter (the stacked adaLN Linears:
+// events x 9920 x ctx): 128 x 128 x 16 tiles, 8 x 8 outputs per thread as four 4 x 4 quadrants, 128-bit global
+// loads prefetched into registers while the current k-slab is multiplied.  Requires K % 16 == 0, lda/ldw % 4 == 0
+// and 16-byte aligned A / W; no residual in the epilogue.
+template <typename OutT>
+__global__ void __launch_bounds__(256, 2) gemm_f32_big_kernel(const float* __restrict__ A, int lda,
+                                                              const float* __restrict__ W, int ldw,
+                                                              OutT* C, int ldc, int M, int N, int K, GemmEpilogue ep) {
+    constexpr int BM = 128, BN = 128, BK = 16, LD = BM + 4;
+    __shared__ __align__(16) float As[BK][LD];
+    __shared__ __align__(16) float Ws[BK][LD];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    // loader: thread -> (row lr + 64 i, k quad lq); rows past the end re-read the last valid row (never stored)
+    const int lr = tid >> 2, lq = (tid & 3) * 4;
+    const float* ap[2]; const float* wp[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        ap[i] = A + (size_t)min(m0 + lr + 64 * i, M - 1) * lda + lq;
+        wp[i] = W + (size_t)min(n0 + lr + 64 * i, N - 1) * ldw + lq;
+    }
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    float4 pa[2], pw[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { pa[i] = *reinterpret_cast<const float4*>(ap[i]); pw[i] = __ldg(reinterpret_cast<const float4*>(wp[i])); }
+    for (int k0 = 0; k0 < K; k0 += BK) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int r = lr + 64 * i;
+            As[lq][r] = pa[i].x; As[lq + 1][r] = pa[i].y; As[lq + 2][r] = pa[i].z; As[lq + 3][r] = pa[i].w;
+            Ws[lq][r] = pw[i].x; Ws[lq + 1][r] = pw[i].y; Ws[lq + 2][r] = pw[i].z; Ws[lq + 3][r] = pw[i].w;
+        }
+        __syncthreads();
+        if (k0 + BK < K) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) { pa[i] = *reinterpret_cast<const float4*>(ap[i] + k0 + BK); pw[i] = __ldg(reinterpret_cast<const float4*>(wp[i] + k0 + BK)); }
+        }
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]), a1 = *reinterpret_cast<const float4*>(&As[kk][64 + ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Ws[kk][tx * 4]), b1 = *reinterpret_cast<const float4*>(&Ws[kk][64 + tx * 4]);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int row = m0 + (i >> 2) * 64 + ty * 4 + (i & 3);
+        if (row >= M) continue;
+        const int ev = ep.row_event ? ep.row_event[row] : row;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int col = n0 + (j >> 2) * 64 + tx * 4 + (j & 3);
+            if (col >= N) continue;
+            float v = acc[i][j];
+            if (ep.bias) v += __ldg(ep.bias + col);
+            if (ep.row_bias) v += ep.row_bias[(size_t)ev * ep.ld_row_bias + col];
+            if (ep.act == 1) v = leaky_relu(v);
+            store_out(C + (size_t)row * ldc + col, v);
+        }
+    }
+}
+
+// copies the per-event rows of event e0 (computed once when every event of the pass shares the evaluation time) to the
+// other events of the pass: temb | ev_a | ev_stats | layer_out
+struct BroadcastPrepParams { float* buf[4]; int len[4]; int e0; };
+__global__ void __launch_bounds__(128) broadcast_prep_kernel(BroadcastPrepParams p) {
+    const int e = p.e0 + 1 + blockIdx.x;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const float* src = p.buf[a] + (size_t)p.e0 * p.len[a];
+        float* dst = p.buf[a] + (size_t)e * p.len[a];
+        for (int i = threadIdx.x; i < p.len[a]; i += blockDim.x) dst[i] = src[i];
+    }
+}
+
 // ------------------------------------------------------------------------------------
 // 5. LayerNorm (+ affine) (+ adaLN modulate) (+ second, non-affine LayerNorm)
 //    one warp per row, row held in registers, two-pass statistics in fp32.

@@ -105,6 +105,7 @@ struct SrhepHandle {
     float* bqkv = nullptr;              // [layers][3h]
     float* wmod = nullptr;              // [mod_width, ctx]   all adaLN Linears stacked
     float* bmod = nullptr;              // [mod_width]
+    float* mod_tbias = nullptr;         // [mod_width]   bmod + the time-embedding columns' contribution (sampling passes share t)
     float* r1 = nullptr;                // 4 x kMaxHid: row sums of the context part of the embed nets' first Linear
     Bf16Weights bw;                     // bf16 re-packed GEMM operands (SRHEP_PREC_BF16)
     int mod_width = 0;
@@ -260,8 +261,15 @@ struct Engine {
     template <typename OutT>
     void gemm_f32(const float* A, int lda, const float* Wt, int ldw, OutT* C, int ldc, int M, int N, int K, const GemmEpilogue& ep) {
         if (rc || M <= 0) return;
-        dim3 grid((M + 63) / 64, (N + 63) / 64);
-        gemm_f32_kernel<OutT><<<grid, 256, 0, s>>>(A, lda, Wt, ldw, C, ldc, M, N, K, ep);
+        const bool big = M >= 256 && N >= 1024 && K % 16 == 0 && lda % 4 == 0 && ldw % 4 == 0 && !ep.resid &&
+                         ((uintptr_t)A & 15) == 0 && ((uintptr_t)Wt & 15) == 0;
+        if (big) {
+            dim3 grid((M + 127) / 128, (N + 127) / 128);
+            gemm_f32_big_kernel<OutT><<<grid, 256, 0, s>>>(A, lda, Wt, ldw, C, ldc, M, N, K, ep);
+        } else {
+            dim3 grid((M + 63) / 64, (N + 63) / 64);
+            gemm_f32_kernel<OutT><<<grid, 256, 0, s>>>(A, lda, Wt, ldw, C, ldc, M, N, K, ep);
+        }
         check("gemm_f32");
     }
 
@@ -338,7 +346,17 @@ struct Engine {
             q.layer_table = W(L.layer_table); q.layer_emb_dim = d.layer_emb_dim;
             q.temb = h->temb; q.ev_a = h->ev_a; q.ev_stats = h->ev_stats; q.layer_out = h->layer_out;
             q.stage = st; q.e0 = p.e0;
-            if (!rc) { event_prep_kernel<<<nE, 128, 0, s>>>(q); check("event_prep"); }
+            // a sampling pass evaluates every event at the same time t: the timestep embedding and everything derived from it
+            // alone is computed for ONE event and copied to the others (per-event times: srhep_velocity with t_event)
+            const bool shared_t = st.t_event == nullptr;             // also for a single event: results must not depend on how a batch is cut into passes
+            if (!rc) { event_prep_kernel<<<shared_t ? 1 : nE, 128, 0, s>>>(q); check("event_prep"); }
+            if (shared_t && nE > 1 && !rc) {
+                BroadcastPrepParams b;
+                b.buf[0] = h->temb; b.len[0] = d.t_emb; b.buf[1] = h->ev_a; b.len[1] = 3 * kMaxHid;
+                b.buf[2] = h->ev_stats; b.len[2] = 2; b.buf[3] = h->layer_out; b.len[3] = 3 * d.layer_out;
+                b.e0 = p.e0;
+                broadcast_prep_kernel<<<nE - 1, 128, 0, s>>>(b); check("broadcast_prep");
+            }
         }
         const bool embed_tc = lp && h->bw.embed_tc && !h->sw.no_embed_tc;
         if (M > 0 && embed_tc) {   // 2. per-cell embeddings on the tensor core (kernels_embed.cuh)
@@ -378,9 +396,19 @@ struct Engine {
         }
         cat = SRHEP_CAT_ADALN;
         {   // 4. every adaLN Linear of the evaluation in one GEMM; 5. context part of feat_0
-            GemmEpilogue ep; ep.bias = h->bmod;
-            gemm_f32<float>(h->silu_ctx + (size_t)p.e0 * d.ctx, d.ctx, h->wmod, d.ctx, h->mod + (size_t)p.e0 * h->mod_width, h->mod_width,
-                            nE, h->mod_width, d.ctx, ep);
+            const float* sc = h->silu_ctx + (size_t)p.e0 * d.ctx;
+            float* mo = h->mod + (size_t)p.e0 * h->mod_width;
+            if (st.t_event == nullptr && d.t_emb % 16 == 0 && (d.ctx - d.t_emb) % 16 == 0) {
+                // shared evaluation time: context = [time_emb | cond mean], so the time columns contribute the same vector to
+                // every event: bias' = b + W[:, :t_emb] silu(time_emb) once, then only the cond columns per event
+                GemmEpilogue e0; e0.bias = h->bmod;
+                gemm_f32<float>(sc, d.ctx, h->wmod, d.ctx, h->mod_tbias, h->mod_width, 1, h->mod_width, d.t_emb, e0);
+                GemmEpilogue ep; ep.bias = h->mod_tbias;
+                gemm_f32<float>(sc + d.t_emb, d.ctx, h->wmod + d.t_emb, d.ctx, mo, h->mod_width, nE, h->mod_width, d.ctx - d.t_emb, ep);
+            } else {
+                GemmEpilogue ep; ep.bias = h->bmod;
+                gemm_f32<float>(sc, d.ctx, h->wmod, d.ctx, mo, h->mod_width, nE, h->mod_width, d.ctx, ep);
+            }
             GemmEpilogue e2; e2.bias = W(L.feat0.b);
             gemm_f32<float>(h->ctx + (size_t)p.e0 * d.ctx, d.ctx, W(L.feat0.w) + ncol, L.feat0.in, h->f0bias + (size_t)p.e0 * d.h_dim, d.h_dim,
                             nE, d.h_dim, d.ctx, e2);
@@ -692,6 +720,7 @@ int srhep_create(int device, const SrhepDims* dims, const float* weights_host, s
         memcpy(&bm[(size_t)d.layers * 6 * H], weights_host + L.vada.b, (size_t)2 * d.v_in * sizeof(float));
         CKC(cudaMalloc(&h->wmod, wm.size() * sizeof(float)));
         CKC(cudaMalloc(&h->bmod, bm.size() * sizeof(float)));
+        CKC(cudaMalloc(&h->mod_tbias, bm.size() * sizeof(float)));
         CKC(cudaMemcpy(h->wmod, wm.data(), wm.size() * sizeof(float), cudaMemcpyHostToDevice));
         CKC(cudaMemcpy(h->bmod, bm.data(), bm.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
@@ -727,7 +756,7 @@ int srhep_destroy(SrhepHandle* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     drop_graphs(h);
-    void* ptrs[] = {h->w, h->wqkv, h->bqkv, h->wmod, h->bmod, h->r1, h->cu_dev, h->row_event, h->chunk_event, h->chunk_row, h->chunk_len,
+    void* ptrs[] = {h->w, h->wqkv, h->bqkv, h->wmod, h->bmod, h->mod_tbias, h->r1, h->cu_dev, h->row_event, h->chunk_event, h->chunk_row, h->chunk_len,
                     h->ev_chunk_start, h->attn_work, h->temb, h->ev_a, h->ev_stats, h->layer_out, h->ctx, h->silu_ctx, h->mod, h->f0bias,
                     h->partial, h->t_fill, h->tok_feat, h->xres, h->qkv, h->h1buf, h->act_a, h->act_b, h->qkv_lp, h->y_a, h->y_b, h->y_tmp,
                     h->ybuf2, h->red_dev, h->sp_dev, h->stage_idx_dev, h->tap_layers, h->tap_feat0, h->tap_final};
