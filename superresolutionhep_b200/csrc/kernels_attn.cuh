@@ -218,8 +218,11 @@ __global__ void __launch_bounds__(kAtt2Threads, 2) attn2_bf16_kernel(const __gri
         const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
         constexpr int fp16 = kFp16 ? 1 : 0;
         uint32_t it = 0, item_i = 0;
+        // the descriptor of the NEXT item is fetched while this one is processed: its L2 round trip sat on the critical path of every item (10 % of the softmax warps' time)
+        AttnItem a_next = (int)blockIdx.x < p.n_items ? p.items[blockIdx.x] : AttnItem{0, 0, 0, 0};
         for (int w = blockIdx.x; w < p.n_items; w += gridDim.x, ++item_i) {
-            const AttnItem a = p.items[w];
+            const AttnItem a = a_next;
+            if (w + (int)gridDim.x < p.n_items) a_next = p.items[w + gridDim.x];
             const int n_kv = (a.k_len + kAtt2KvTile - 1) / kAtt2KvTile;
             float m_ref = -INFINITY, l = 0.f;
             // query rows past the event's end (the last 128-row tile of an event is ragged): a warp whose 32 rows are all padding
