@@ -68,7 +68,7 @@ struct EventPrepParams {
     int e0;
 };
 
-__global__ void __launch_bounds__(128) event_prep_kernel(EventPrepParams p) {
+__global__ void __launch_bounds__(512) event_prep_kernel(EventPrepParams p) {
     __shared__ float s_sin[kMaxFreq];
     __shared__ float s_h[kMaxTemb];
     __shared__ float s_temb[kMaxTemb];
@@ -716,16 +716,17 @@ __global__ void __launch_bounds__(256) head_prep_kernel(HeadPrepParams p, OutT* 
     }
 }
 
-// float4 variant for the shipped dimensions (h = 256, cond = 96, ctx = 160) on the blocked residual layout: same mapping
-// (one warp per row, 8 rows per block) but every lane owns groups of 4 consecutive columns, so a row costs ~25 128-bit
-// memory instructions per lane instead of ~90 scalar ones (the scalar kernel is issue-bound: 64 % issue slots, 60 % LSU).
-// Pieces: h -> 2 per lane (cols 4 lane + 128 j); cond -> 1 (lanes 0-23); ctx -> 1 + 1 (lanes 0-7).  All row pointers 16-byte aligned.
+// float4 kernel for the shipped dimensions (h = 256, cond = 96, ctx = 160) on the blocked residual layout: one warp per
+// row at a time, every lane owns groups of 4 consecutive columns (h -> 2 pieces per lane at cols 4 lane + 128 j; cond -> 1,
+// lanes 0-23; ctx -> 1 + 1, lanes 0-7; all row pointers 16-byte aligned), eight rows per warp: the two LayerNorms'
+// parameter vectors (10 float4 per lane) stay in registers for
+// all of them and the event's adaLN shift / scale rows (6 float4) are re-read only when the event changes, so a row costs
+// 10 memory instructions per lane instead of 26 (the one-row-per-warp version ran at 56 % of the L1 wavefront rate and 50 %
+// of the issue slots, almost all of it re-loading parameters).  Row i of the block's 64 = 8 i + warp: the 8 warps still cover 8
+// consecutive rows (256 contiguous bytes per column group of the blocked residual) in every iteration.
 template <typename OutT>
 __global__ void __launch_bounds__(256) head_prep_v4_kernel(HeadPrepParams p, OutT* hin, int ldh) {
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (row >= p.M) return;
-    const int ev = p.row_event[row];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool hc = lane < 24, hx1 = lane < 8;
     auto ld4 = [](const float* q) { return *reinterpret_cast<const float4*>(q); };
     auto st4 = [](OutT* q, float4 v) {
@@ -740,32 +741,60 @@ __global__ void __launch_bounds__(256) head_prep_v4_kernel(HeadPrepParams p, Out
     auto mod4 = [](float4 v, float4 sc, float4 sh) { return make_float4(fmaf(v.x, 1.f + sc.x, sh.x), fmaf(v.y, 1.f + sc.y, sh.y), fmaf(v.z, 1.f + sc.z, sh.z), fmaf(v.w, 1.f + sc.w, sh.w)); };
     auto nrm4 = [](float4 v, float m, float r) { return make_float4((v.x - m) * r, (v.y - m) * r, (v.z - m) * r, (v.w - m) * r); };
     const int c0 = lane * 4, c1 = 128 + lane * 4;
-    float4 a0 = ld4(p.x + xblk_index(row, c0)), a1 = ld4(p.x + xblk_index(row, c1));
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 cc = hc ? ld4(p.tok_feat + (size_t)row * p.ldt + c0) : z4;
-    const float* cx = p.ctx + (size_t)ev * 160;
-    float4 x0 = ld4(cx + c0), x1 = hx1 ? ld4(cx + c1) : z4;
-    const float* sh = p.shift + (size_t)ev * p.ld_mod; const float* sc = p.scale + (size_t)ev * p.ld_mod;
-    // final_norm over h = 256
-    float mean = warp_sum(sum4(a0) + sum4(a1)) * (1.0f / 256.f);
-    float rstd = 1.0f / sqrtf(warp_sum(sq4(a0, mean) + sq4(a1, mean)) * (1.0f / 256.f) + kLnEps);
-    a0 = aff4(a0, mean, rstd, ld4(p.fn_w + c0), ld4(p.fn_b + c0));
-    a1 = aff4(a1, mean, rstd, ld4(p.fn_w + c1), ld4(p.fn_b + c1));
-    if (p.final_tap) { *reinterpret_cast<float4*>(p.final_tap + (size_t)row * 256 + c0) = a0; *reinterpret_cast<float4*>(p.final_tap + (size_t)row * 256 + c1) = a1; }
-    // norm_v_t over h + cond = 352, affine, modulate
-    mean = warp_sum(sum4(a0) + sum4(a1) + sum4(cc)) * (1.0f / 352.f);
-    rstd = 1.0f / sqrtf(warp_sum(sq4(a0, mean) + sq4(a1, mean) + (hc ? sq4(cc, mean) : 0.f)) * (1.0f / 352.f) + kLnEps);
-    a0 = mod4(aff4(a0, mean, rstd, ld4(p.nv_w + c0), ld4(p.nv_b + c0)), ld4(sc + c0), ld4(sh + c0));
-    a1 = mod4(aff4(a1, mean, rstd, ld4(p.nv_w + c1), ld4(p.nv_b + c1)), ld4(sc + c1), ld4(sh + c1));
-    if (hc) cc = mod4(aff4(cc, mean, rstd, ld4(p.nv_w + 256 + c0), ld4(p.nv_b + 256 + c0)), ld4(sc + 256 + c0), ld4(sh + 256 + c0));
-    // LayerNorm (no affine) over v_in + ctx = 512
-    mean = warp_sum(sum4(a0) + sum4(a1) + sum4(cc) + sum4(x0) + sum4(x1)) * (1.0f / 512.f);
-    rstd = 1.0f / sqrtf(warp_sum(sq4(a0, mean) + sq4(a1, mean) + (hc ? sq4(cc, mean) : 0.f) + sq4(x0, mean) + (hx1 ? sq4(x1, mean) : 0.f)) * (1.0f / 512.f) + kLnEps);
-    OutT* o = hin + (size_t)row * ldh;
-    st4(o + c0, nrm4(a0, mean, rstd)); st4(o + c1, nrm4(a1, mean, rstd));
-    if (hc) st4(o + 256 + c0, nrm4(cc, mean, rstd));
-    st4(o + 352 + c0, nrm4(x0, mean, rstd));
-    if (hx1) st4(o + 352 + c1, nrm4(x1, mean, rstd));
+    const float4 fw0 = ld4(p.fn_w + c0), fw1 = ld4(p.fn_w + c1), fb0 = ld4(p.fn_b + c0), fb1 = ld4(p.fn_b + c1);
+    const float4 nw0 = ld4(p.nv_w + c0), nw1 = ld4(p.nv_w + c1), nb0 = ld4(p.nv_b + c0), nb1 = ld4(p.nv_b + c1);
+    const float4 nwc = hc ? ld4(p.nv_w + 256 + c0) : z4, nbc = hc ? ld4(p.nv_b + 256 + c0) : z4;
+    int ev_prev = -1;
+    float4 sc0 = z4, sc1 = z4, scc = z4, sh0 = z4, sh1 = z4, shc = z4, x0 = z4, x1 = z4;
+    // the next row's data is requested before this row's three dependent reduction rounds start
+    const int row_first = blockIdx.x * 64 + warp;
+    float4 na0 = z4, na1 = z4, ncc = z4; int nev = 0;
+    if (row_first < p.M) {
+        na0 = ld4(p.x + xblk_index(row_first, c0)); na1 = ld4(p.x + xblk_index(row_first, c1));
+        ncc = hc ? ld4(p.tok_feat + (size_t)row_first * p.ldt + c0) : z4;
+        nev = p.row_event[row_first];
+    }
+#pragma unroll 1
+    for (int i = 0; i < 8; ++i) {
+        const int row = row_first + i * 8;
+        if (row >= p.M) break;
+        const int ev = nev;
+        float4 a0 = na0, a1 = na1, cc = ncc;
+        if (i + 1 < 8 && row + 8 < p.M) {
+            na0 = ld4(p.x + xblk_index(row + 8, c0)); na1 = ld4(p.x + xblk_index(row + 8, c1));
+            ncc = hc ? ld4(p.tok_feat + (size_t)(row + 8) * p.ldt + c0) : z4;
+            nev = p.row_event[row + 8];
+        }
+        if (ev != ev_prev) {                                   // warp-uniform
+            const float* cx = p.ctx + (size_t)ev * 160;
+            x0 = ld4(cx + c0); x1 = hx1 ? ld4(cx + c1) : z4;
+            const float* sh = p.shift + (size_t)ev * p.ld_mod; const float* sc = p.scale + (size_t)ev * p.ld_mod;
+            sc0 = ld4(sc + c0); sc1 = ld4(sc + c1); sh0 = ld4(sh + c0); sh1 = ld4(sh + c1);
+            if (hc) { scc = ld4(sc + 256 + c0); shc = ld4(sh + 256 + c0); }
+            ev_prev = ev;
+        }
+        // final_norm over h = 256
+        float mean = warp_sum(sum4(a0) + sum4(a1)) * (1.0f / 256.f);
+        float rstd = 1.0f / sqrtf(warp_sum(sq4(a0, mean) + sq4(a1, mean)) * (1.0f / 256.f) + kLnEps);
+        a0 = aff4(a0, mean, rstd, fw0, fb0);
+        a1 = aff4(a1, mean, rstd, fw1, fb1);
+        if (p.final_tap) { *reinterpret_cast<float4*>(p.final_tap + (size_t)row * 256 + c0) = a0; *reinterpret_cast<float4*>(p.final_tap + (size_t)row * 256 + c1) = a1; }
+        // norm_v_t over h + cond = 352, affine, modulate
+        mean = warp_sum(sum4(a0) + sum4(a1) + sum4(cc)) * (1.0f / 352.f);
+        rstd = 1.0f / sqrtf(warp_sum(sq4(a0, mean) + sq4(a1, mean) + (hc ? sq4(cc, mean) : 0.f)) * (1.0f / 352.f) + kLnEps);
+        a0 = mod4(aff4(a0, mean, rstd, nw0, nb0), sc0, sh0);
+        a1 = mod4(aff4(a1, mean, rstd, nw1, nb1), sc1, sh1);
+        if (hc) cc = mod4(aff4(cc, mean, rstd, nwc, nbc), scc, shc);
+        // LayerNorm (no affine) over v_in + ctx = 512
+        mean = warp_sum(sum4(a0) + sum4(a1) + sum4(cc) + sum4(x0) + sum4(x1)) * (1.0f / 512.f);
+        rstd = 1.0f / sqrtf(warp_sum(sq4(a0, mean) + sq4(a1, mean) + (hc ? sq4(cc, mean) : 0.f) + sq4(x0, mean) + (hx1 ? sq4(x1, mean) : 0.f)) * (1.0f / 512.f) + kLnEps);
+        OutT* o = hin + (size_t)row * ldh;
+        st4(o + c0, nrm4(a0, mean, rstd)); st4(o + c1, nrm4(a1, mean, rstd));
+        if (hc) st4(o + 256 + c0, nrm4(cc, mean, rstd));
+        st4(o + 352 + c0, nrm4(x0, mean, rstd));
+        if (hx1) st4(o + 352 + c1, nrm4(x1, mean, rstd));
+    }
 }
 
 // ------------------------------------------------------------------------------------

@@ -314,7 +314,7 @@ struct Engine {
         const int grid = (q.M + 7) / 8;
         const int ph = d.h_dim / 32, pc = d.cond / 32, px = d.ctx / 32;
         if (ph == 8 && pc == 3 && px == 5 && q.x_blocked && sizeof(OutT) == 2 && q.ldt % 4 == 0 && is_lp(h) && !h->sw.head_prep_scalar) {
-            head_prep_v4_kernel<OutT><<<grid, 256, 0, s>>>(q, hin, ldh);
+            head_prep_v4_kernel<OutT><<<(q.M + 63) / 64, 256, 0, s>>>(q, hin, ldh);
             check("head_prep_v4");
             return;
         }
@@ -349,7 +349,7 @@ struct Engine {
             // a sampling pass evaluates every event at the same time t: the timestep embedding and everything derived from it
             // alone is computed for ONE event and copied to the others (per-event times: srhep_velocity with t_event)
             const bool shared_t = st.t_event == nullptr;             // also for a single event: results must not depend on how a batch is cut into passes
-            if (!rc) { event_prep_kernel<<<shared_t ? 1 : nE, 128, 0, s>>>(q); check("event_prep"); }
+            if (!rc) { event_prep_kernel<<<shared_t ? 1 : nE, shared_t ? 512 : 128, 0, s>>>(q);   /* the single block is pure latency: 16 warps shorten its matvec loops */ check("event_prep"); }
             if (shared_t && nE > 1 && !rc) {
                 BroadcastPrepParams b;
                 b.buf[0] = h->temb; b.len[0] = d.t_emb; b.buf[1] = h->ev_a; b.len[1] = 3 * kMaxHid;

@@ -214,3 +214,25 @@ def test_cost_balanced_shards_concatenate_to_whole():
         xs = m.generate_samples(to_dev(sub), n_steps=4, method="euler", x0=x0[a:b, : sub["q_mask"].shape[1]].cuda()).cpu()
         parts.append(xs[..., 0][sub["q_mask"]])
     assert torch.equal(torch.cat(parts), whole[..., 0][mask])
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_shared_time_path_equals_per_event_time_path(precision):
+    """A sampling pass evaluates every event at the same t: the timestep embedding is computed for one event and
+    copied, and the time columns of the adaLN contraction are folded into its bias (srhep.cu: enqueue_eval).
+    ``forward`` takes a time per event and uses the general path.  One Euler step from the sampler must reproduce
+    ``x0 + dt * forward(x0, t0)``: the two paths differ only in fp32 summation order."""
+    m, _, _ = make_model("single_e", 7, precision=precision)
+    counts = np.array([124, 256, 4, 300, 804])
+    batch = synthetic_events("single_e", len(counts), seed=11, counts=counts)
+    x0 = synthetic_noise(batch, seed=3)
+    db = to_dev(batch)
+    mask = batch["q_mask"]
+    n_steps = 5
+    xs = m.generate_samples(db, n_steps=n_steps, method="euler", ret_seq=True, x0=x0.cuda())
+    dt = 1.0 / (n_steps - 1)
+    v = m(db, x0.cuda(), torch.zeros(len(counts), device="cuda"))
+    want = packed(x0, mask) + dt * packed(v.cpu(), mask)
+    got = packed(xs[1].cpu(), mask)
+    tol = 2e-5 if precision == "fp32" else 2e-3      # 16-bit operands: a last-bit difference of the adaLN rows moves a rounding boundary now and then
+    close(got, want, tol, tol, f"shared-t vs per-event-t ({precision})")
