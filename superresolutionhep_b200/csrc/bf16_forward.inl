@@ -169,6 +169,10 @@ int bf16_pack_weights(SrhepHandle* h, const float* wh) {
     CK(h, cudaFuncSetAttribute(layer_chain_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CK(h, cudaFuncSetAttribute(layer_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemBytes));
     CK(h, cudaFuncSetAttribute(layer_chain_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(h, cudaFuncSetAttribute(layer_chain_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemBytes));
+    CK(h, cudaFuncSetAttribute(layer_chain_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(h, cudaFuncSetAttribute(layer_chain_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemBytes));
+    CK(h, cudaFuncSetAttribute(layer_chain_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CK(h, cudaFuncSetAttribute(gemm_bf16_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_bf16_smem_bytes<128>(hk / 64)));
     return 0;
 }
@@ -300,6 +304,33 @@ void launch_chain(Engine& E, int M, int l, const int* rev) {
     }
 }
 
+// feat_0 -> LN1 . modulate of layer 0 -> q|k|v of layer 0 in ONE launch: the chain kernel in its first-layer mode (stages
+// feat_0, q, k, v).  Replaces the feat_0 GEMM and the layer-0 q|k|v GEMM: the LayerNorm output never travels through HBM.
+void launch_chain_first(Engine& E, int M, const int* rev) {
+    if (E.rc || M <= 0) return;
+    SrhepHandle* h = E.h;
+    const SrhepDims& d = h->d; Bf16Weights& bw = h->bw;
+    const int H = d.h_dim;
+    ChainParams q{};
+    q.M = M; q.n_stages = 4; q.fp16 = h->precision == SRHEP_PREC_FP16;
+    q.row_event = rev; q.x = h->xres;
+    q.w[0] = bw.img + bw.feat0;
+    for (int j = 0; j < 3; ++j) q.w[1 + j] = bw.img + bw.qkv[0] + (size_t)j * H * H * 2;
+    // cst[2] (bias of the residual-producing stage) stays zero: feat_0's bias is inside the per-event rows
+    memcpy(q.cst[3], bw.bqkv_h, 3 * H * sizeof(float));
+    memcpy(q.cst[8], bw.bias_h + 3 * H, 2 * H * sizeof(float));        // layer 0 norm1 w | b
+    q.row_bias = h->f0bias; q.ld_row_bias = H;
+    q.shift_nxt = h->mod; q.scale_nxt = h->mod + H;                    // layer 0 shift_msa | scale_msa
+    q.gate_msa = q.shift_mlp = q.scale_mlp = q.gate_mlp = h->mod;      // unused in this mode
+    q.ld_mod = h->mod_width;
+    q.qkv = h->qkv_lp;
+    const int m_tiles = (M + 127) / 128;
+    const int grid = std::max(1, std::min(m_tiles, 2 * 148));
+    if (q.fp16) layer_chain_kernel<true, true><<<grid, kChainThreads, kChainSmemBytes, E.s>>>(bw.tm_tok, q);
+    else layer_chain_kernel<false, true><<<grid, kChainThreads, kChainSmemBytes, E.s>>>(bw.tm_tok, q);
+    E.check("layer_chain_first");
+}
+
 void bf16_forward(Engine& E, const Pass& p, const int* rev, const StageRef& st) {
     SrhepHandle* h = E.h;
     const SrhepDims& d = h->d; const Layout& L = h->L; Bf16Weights& bw = h->bw;
@@ -321,6 +352,9 @@ void bf16_forward(Engine& E, const Pass& p, const int* rev, const StageRef& st) 
         if (!second) { ep.ln_w = bl + 3 * H; ep.ln_b = bl + 4 * H; ep.ln_shift = ml; ep.ln_scale = ml + H; }
         else { ep.ln_w = bl + 5 * H; ep.ln_b = bl + 6 * H; ep.ln_shift = ml + 3 * H; ep.ln_scale = ml + 4 * H; }
     };
+    const bool first_fused = chain && bw.feat0_kpad == 192 && !h->sw.no_chain_first;
+    if (first_fused) launch_chain_first(E, M, rev);
+    else
     { GemmEpilogue ep; ep.row_bias = h->f0bias; ep.ld_row_bias = H; ep.row_event = rev; ep.act = 1;
       with_ln(ep, 0, false);
       launch_gemm_bf16<256, true>(E, bw.tm_tok, M, bw.feat0_kpad, H, bw.img + bw.feat0, x, H, 0, ep); }
@@ -328,6 +362,7 @@ void bf16_forward(Engine& E, const Pass& p, const int* rev, const StageRef& st) 
     if (chain) {
         // layer 0's q|k|v come from the feat_0 GEMM's fused LN1; every later projection rides in the previous layer's chain kernel
         E.cat = SRHEP_CAT_QKV;
+        if (!first_fused)
         { GemmEpilogue ep; ep.bias = h->bqkv;
           launch_gemm_bf16<256>(E, bw.tm_ln, M, H, 3 * H, bw.img + bw.qkv[0], qkv, 3 * H, 1, ep); }
         for (int l = 0; l < d.layers; ++l) {

@@ -45,6 +45,7 @@ struct ChainParams {
     const float* shift_mlp; const float* scale_mlp; const float* gate_mlp;
     const float* shift_nxt; const float* scale_nxt;       // next layer's shift_msa / scale_msa
     int ld_mod;
+    const float* row_bias; int ld_row_bias;   // first-layer mode only: per-event bias rows of feat_0 (its context part)
     void* qkv;                   // [M, 768] 16-bit q|k|v of the next layer
     long long* dbg;              // optional timeline of CTA 0 (clock64 stamps, 32 per tile, first 8 tiles); null in production
 };
@@ -70,6 +71,22 @@ __device__ __forceinline__ void chain_resid_chunk(uint32_t (&r)[32], const float
             float w = __uint_as_float(r[j + u]) + bb[u];
             if (kAct) w = leaky_relu(w);
             w = fmaf(gg[u], w, xr[j + u]);
+            s1 += w; s2 = fmaf(w, w, s2);
+            r[j + u] = __float_as_uint(w);
+        }
+    }
+}
+
+// first-layer mode: leaky(acc + bias + per-event bias) IS the residual row (feat_0, models/flow_model.py:224-228)
+__device__ __forceinline__ void chain_first_chunk(uint32_t (&r)[32], const float* bias /*constant bank*/, bool staged, uint32_t rb_sm, const float* __restrict__ rb,
+                                                  float& s1, float& s2) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+        const float4 b4 = par_f4(staged, rb_sm + j * 4, rb + j);
+        const float bb[4] = {bias[j] + b4.x, bias[j + 1] + b4.y, bias[j + 2] + b4.z, bias[j + 3] + b4.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float w = leaky_relu(__uint_as_float(r[j + u]) + bb[u]);
             s1 += w; s2 = fmaf(w, w, s2);
             r[j + u] = __float_as_uint(w);
         }
@@ -139,7 +156,7 @@ __device__ __forceinline__ void transpose_line_pieces(uint32_t (&a)[32], int lan
 #define CHAIN_STAMP(tile, k) do { } while (0)
 #endif
 
-template <bool kFp16>
+template <bool kFp16, bool kFirst = false>
 __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ ChainParams p) {
     extern __shared__ __align__(1024) uint8_t chain_smem[];      // no static smem in this kernel: the dynamic window starts 1024-aligned
     uint8_t* s_a = chain_smem;
@@ -159,7 +176,9 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tiles = (p.M + 127) / 128;
     constexpr uint32_t kTmemCols = 256;
-    const int slots_per_tile = p.n_stages * 8;
+    // first-layer mode (kFirst): the stages are feat_0 (K = 192: three k-blocks; epilogue = stage 2's without a residual to read), q, k, v
+    constexpr int kKb0 = kFirst ? 3 : 4;                 // k-blocks of stage 0
+    const int slots_per_tile = p.n_stages * 8 - (kFirst ? 2 : 0);
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_a);
@@ -183,18 +202,22 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                     if (j == (tile_i == 0 ? 0 : 2)) {                 // the A tile: first thing of the kernel, else after two weight slots of run-ahead
                         if (tile_i > 0) mbar_wait(a_free, (tile_i - 1) & 1);
                         CHAIN_STAMP(tile_i, 0);
-                        mbar_expect_tx(a_full, kChainABytes);
+                        mbar_expect_tx(a_full, kKb0 * 16384);
 #pragma unroll
-                        for (int kb = 0; kb < 4; ++kb) tma_load_2d(s_a + kb * 16384, &tmap_a, a_full, kb * 64, t * 128);
+                        for (int kb = 0; kb < kKb0; ++kb) tma_load_2d(s_a + kb * 16384, &tmap_a, a_full, kb * 64, t * 128);
                         CHAIN_STAMP(tile_i, 1);
+                        if (!kFirst) {
                         // the fp32 residual tile of THIS tile (128 KB contiguous in the blocked layout) is first needed by the
                         // stage-0 epilogue, several microseconds from now: pull it into L2 meanwhile
                         const float* xt = p.x + (size_t)t * 128 * kChainH;
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
                             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(xt + i * 8192), "r"(32768u) : "memory");
+                        }
                     }
-                    const int g = j >> 3, nh = (j >> 2) & 1, kb = j & 3;      // column half outer: the two halves of the accumulator are a double buffer
+                    int g, nh, kb;                                            // column half outer: the two halves of the accumulator are a double buffer
+                    if (kFirst && j < 6) { g = 0; nh = j / 3; kb = j % 3; }
+                    else { const int jj = kFirst ? j + 2 : j; g = jj >> 3; nh = (jj >> 2) & 1; kb = jj & 3; }
                     const uint32_t s = slot_it % kChainSlots, ph = (slot_it / kChainSlots) & 1;
                     mbar_wait(&w_empty[s], ph ^ 1);
                     mbar_expect_tx(&w_full[s], kChainSlotBytes);
@@ -212,10 +235,11 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                     if (stage_it > 0) mbar_wait(&epi_done[nh], (stage_it - 1) & 1);
                     if (nh == 0) {
                         if (g == 0) { if (lane == 0) CHAIN_STAMP(tile_i, 2); mbar_wait(a_full, tile_i & 1); if (lane == 0) CHAIN_STAMP(tile_i, 3); }
-                        else if (g <= 3) { mbar_wait(a_written, aw_it & 1); ++aw_it; }      // stages 1-3 read the A operand the previous epilogue wrote
+                        else if (kFirst ? g == 1 : g <= 3) { mbar_wait(a_written, aw_it & 1); ++aw_it; }      // stages 1-3 (first-layer mode: stage 1) read the A operand the previous epilogue wrote
                     }
                     tc_fence_after();
-                    for (int kb = 0; kb < 4; ++kb, ++slot_it) {
+                    const int kbn = (kFirst && g == 0) ? kKb0 : 4;
+                    for (int kb = 0; kb < kbn; ++kb, ++slot_it) {
                         const uint32_t s = slot_it % kChainSlots, ph = (slot_it / kChainSlots) & 1;
                         mbar_wait(&w_full[s], ph);
                         tc_fence_after();
@@ -226,7 +250,7 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                                 umma_bf16(tmem_base + nh * 128, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
                                           (uint32_t)((kb | k) != 0));
                             tc_commit(&w_empty[s]);
-                            if (kb == 3) {
+                            if (kb == kbn - 1) {
                                 tc_commit(&acc_full[nh]);
                                 if (nh == 1 && g == p.n_stages - 1) tc_commit(a_free);
                             }
@@ -270,7 +294,7 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
             // One thread copies the tile's per-event rows of three adaLN arrays into the A buffer once every MMA of the stage has
             // retired (the buffer is dead until this stage's last pass rewrites it); everybody then reads them as shared-memory
             // broadcasts instead of paying an L2 round trip per 32-column chunk.
-            auto stage_rows = [&](const float* a0, const float* a1, const float* a2) {
+            auto stage_rows = [&](const float* a0, const float* a1, const float* a2, int ld0) {
                 if (!staged) return;
                 if (warp == 2 && lane == 0) {
                     const int na = 1 + (a1 != nullptr) + (a2 != nullptr);
@@ -278,7 +302,7 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                     for (int e = 0; e < ne; ++e) {
                         const size_t go = (size_t)(ev0 + e) * p.ld_mod;
                         uint8_t* dst = s_a + 4096 + e * 3072;
-                        bulk_load(dst, a0 + go, 1024, par_full);
+                        bulk_load(dst, a0 + (size_t)(ev0 + e) * ld0, 1024, par_full);
                         if (a1) bulk_load(dst + 1024, a1 + go, 1024, par_full);
                         if (a2) bulk_load(dst + 2048, a2 + go, 1024, par_full);
                     }
@@ -288,7 +312,7 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
             };
 
             // ---------------------------------------------------------------- stage 0: out-projection, residual, LN2 + modulate + LN
-            {
+            if constexpr (!kFirst) {
                 float xr[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) xr[j] = 0.f;
@@ -300,7 +324,7 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                 mbar_wait(&acc_full[hh ^ 1], stage_it & 1);               // every MMA of the stage retired: the A buffer is free for the scratch and the staged rows
                 if (warp == 2 && lane == 0) CHAIN_STAMP(tile_i, 10);
                 tc_fence_after();
-                stage_rows(p.gate_msa, p.scale_mlp, p.shift_mlp);
+                stage_rows(p.gate_msa, p.scale_mlp, p.shift_mlp, p.ld_mod);
                 float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
@@ -358,7 +382,7 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                 stage_done(true);
             }
             // ---------------------------------------------------------------- stage 1: MLP hidden
-            {
+            if constexpr (!kFirst) {
                 mbar_wait(&acc_full[hh], stage_it & 1);
                 mbar_wait(&acc_full[hh ^ 1], stage_it & 1);               // A is rewritten in place: every MMA of the stage must have retired
                 if (warp == 2 && lane == 0) CHAIN_STAMP(tile_i, 12);
@@ -382,7 +406,7 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                 float xr[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) xr[j] = 0.f;
-                if (valid) {
+                if (!kFirst && valid) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) ldg256_stream(xrow + (j >> 3) * 1024, &xr[j]);   // x1, written by this thread in stage 0
                 }
@@ -392,18 +416,19 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                 tc_fence_after();
                 // last layer: the A buffer is handed back to the producer (a_free) as soon as this stage's MMAs retire, so nothing may be staged in it
                 const bool st2 = staged && next;
-                if (st2) stage_rows(p.gate_mlp, p.scale_nxt, p.shift_nxt);
+                if (st2) stage_rows(kFirst ? p.row_bias : p.gate_mlp, p.scale_nxt, p.shift_nxt, kFirst ? p.ld_row_bias : p.ld_mod);
                 float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
                     uint32_t r[32];
                     tmem_ld32(t_col + c * 32, r);
                     tmem_ld_wait();
-                    chain_resid_chunk<true>(r, xr, &p.cst[2][hh * 128 + c * 32], st2, psm + c * 128, p.gate_mlp + eo + c * 32, s1, s2);
+                    if (kFirst) chain_first_chunk(r, &p.cst[2][hh * 128 + c * 32], st2, psm + c * 128, p.row_bias + (size_t)evt * p.ld_row_bias + hh * 128 + c * 32, s1, s2);
+                    else chain_resid_chunk<true>(r, xr, &p.cst[2][hh * 128 + c * 32], st2, psm + c * 128, p.gate_mlp + eo + c * 32, s1, s2);
                     if (valid) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 8) stg256_stream(xrow + (c * 4 + (j >> 3)) * 1024, &r[j]);
-                        if (c < 3) {
+                        if (!kFirst && c < 3) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 8) ldg256_stream(xrow + ((c + 1) * 4 + (j >> 3)) * 1024, &xr[j]);
                         }

@@ -111,7 +111,7 @@ struct SrhepHandle {
     int mod_width = 0;
 
     // diagnostic switches (environment, read once per API call: A/B comparisons in the tests and tools)
-    struct Switches { bool no_chain = false, attn_simt = false, attn_v1 = false, no_lnfuse = false, head_fp32 = false, no_headchain = false, no_embed_tc = false, head_prep_scalar = false, chain_dbg = false, attn_dbg = false; } sw;
+    struct Switches { bool no_chain = false, no_chain_first = false, attn_simt = false, attn_v1 = false, no_lnfuse = false, head_fp32 = false, no_headchain = false, no_embed_tc = false, head_prep_scalar = false, chain_dbg = false, attn_dbg = false; } sw;
     // options
     int64_t pass_tokens = 0;
     int use_graph = 1;
@@ -191,7 +191,7 @@ int dev_alloc(SrhepHandle* h, T*& p, size_t n) {
 bool is_lp(const SrhepHandle* h) { return h->precision != SRHEP_PREC_FP32; }
 void read_switches(SrhepHandle* h) {
     auto on = [](const char* n) { const char* v = getenv(n); return v && *v && *v != '0'; };
-    h->sw.no_chain = on("SRHEP_NO_CHAIN"); h->sw.attn_simt = on("SRHEP_ATTN_SIMT"); h->sw.attn_v1 = on("SRHEP_ATTN_V1");
+    h->sw.no_chain = on("SRHEP_NO_CHAIN"); h->sw.no_chain_first = on("SRHEP_NO_CHAIN_FIRST"); h->sw.attn_simt = on("SRHEP_ATTN_SIMT"); h->sw.attn_v1 = on("SRHEP_ATTN_V1");
     h->sw.no_lnfuse = on("SRHEP_NO_LNFUSE"); h->sw.head_fp32 = on("SRHEP_HEAD_FP32"); h->sw.no_headchain = on("SRHEP_NO_HEADCHAIN"); h->sw.no_embed_tc = on("SRHEP_NO_EMBED_TC"); h->sw.head_prep_scalar = on("SRHEP_HEAD_PREP_SCALAR");
     h->sw.chain_dbg = on("SRHEP_CHAIN_DBG"); h->sw.attn_dbg = on("SRHEP_ATTN_DBG");
 }
