@@ -72,10 +72,13 @@ class PackedEvents:
         self.cu_host = cu.contiguous()
         self.n_events = self.mask.shape[0]
         self.n_cells = int(cu[-1])
+        # flat positions of the real cells, found ONCE: boolean-mask indexing would run nonzero() and synchronise with
+        # the host for every tensor that is packed or unpacked
+        self.idx = torch.nonzero(self.mask.reshape(-1)).squeeze(1)
 
         def take(key, dtype):
             v = batch[key].to(device)
-            return v.reshape(self.mask.shape)[self.mask].to(dtype).contiguous()
+            return v.reshape(-1).index_select(0, self.idx).to(dtype).contiguous()
 
         self.eta = take("eta", torch.float32)
         self.cosphi = take("cosphi", torch.float32)
@@ -88,7 +91,7 @@ class PackedEvents:
                               self.e_proxy.data_ptr(), self.layer.data_ptr())
 
     def pack(self, x: torch.Tensor) -> torch.Tensor:
-        return x.to(self.mask.device).reshape(self.mask.shape)[self.mask].float().contiguous()
+        return x.to(self.mask.device).reshape(-1).index_select(0, self.idx).float().contiguous()
 
     def unpack(self, packed: torch.Tensor, fill: Optional[torch.Tensor] = None) -> torch.Tensor:
         """(..., T) -> (..., B, Nmax, 1)."""
@@ -97,7 +100,7 @@ class PackedEvents:
             out = packed.new_zeros(*lead, *self.mask.shape)
         else:
             out = fill.to(packed.device).reshape(self.mask.shape).expand(*lead, *self.mask.shape).clone()
-        out[..., self.mask] = packed
+        out.reshape(*lead, -1).index_copy_(-1, self.idx, packed)
         return out.unsqueeze(-1)
 
 
