@@ -364,7 +364,7 @@ def _main():
                 "per_category_ms": {c: round(per_cat[c]["ms"], 4) for c in per_cat},
                 "evaluation_tflops": flops_per_eval(counts) / (total_ms * 1e-3) / 1e12 if total_ms else None}
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:          # reported at N = 1 only (under torchrun the host threads are pinned to 1 per rank)
             cores = os.cpu_count() or 1
             val, secs = oracle_events_per_s(args.workload, args.ref_events, args.n_steps)
             cpu = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
