@@ -87,3 +87,31 @@ def test_gather_packed_world2_gloo(counts):
         ret = mgr.dict()
         mp.spawn(_gather_worker, args=(world, _free_port(), list(counts), ret), nprocs=world, join=True)
         assert ret["ok"] is True and ret["none_1"] is True
+
+
+def test_packed_events_pack_unpack_roundtrip():
+    """PackedEvents (flow_model.py) finds the positions of the real cells once and packs / unpacks with index_select /
+    index_copy_: same result as boolean-mask indexing of the padded (B, Nmax, 1) tensors (dataset.py:341-349 layout)."""
+    import torch
+    from superresolutionhep_b200.flow_model import PackedEvents
+    from superresolutionhep_b200.synthetic import synthetic_events
+    counts = np.array([124, 4, 256, 300])
+    batch = synthetic_events("single_e", len(counts), seed=3, counts=counts)
+    ev = PackedEvents(batch, torch.device("cpu"))
+    m = batch["q_mask"]
+    assert ev.n_cells == int(counts.sum()) and ev.cu_host.tolist() == [0] + np.cumsum(counts).tolist()
+    for key in ("eta", "cosphi", "sinphi", "e_proxy"):
+        assert torch.equal(getattr(ev, key), batch[key].reshape(m.shape)[m].float())
+    assert torch.equal(ev.layer, batch["layer"].reshape(m.shape)[m].to(torch.int32))
+    x = torch.randn(batch["e_proxy"].shape)
+    p = ev.pack(x)
+    assert torch.equal(p, x.reshape(m.shape)[m])
+    u = ev.unpack(p)
+    assert u.shape == x.shape and torch.equal(u[..., 0][m], p) and float(u[..., 0][~m].abs().sum()) == 0.0
+    seq = torch.randn(3, ev.n_cells)
+    us = ev.unpack(seq)
+    assert us.shape == (3,) + tuple(x.shape)
+    for j in range(3):
+        assert torch.equal(us[j][..., 0][m], seq[j])
+    uf = ev.unpack(p, fill=torch.full(x.shape, 7.0))
+    assert float(uf[..., 0][~m].min()) == 7.0 and torch.equal(uf[..., 0][m], p)
