@@ -21,9 +21,9 @@ constexpr int kAtt2Threads = 192;
 constexpr int kAtt2Stages = 4;
 constexpr int kAtt2KvTile = 64;
 #ifndef SRHEP_POLY_MASK
-#define SRHEP_POLY_MASK 0xAA
+#define SRHEP_POLY_MASK 0x00
 #endif
-constexpr int kPolyMask = SRHEP_POLY_MASK;          // which of the 8 groups of 4 scores per 32 use the polynomial exp2 for their second pair (0xAA: every other group = 25 %)
+constexpr int kPolyMask = SRHEP_POLY_MASK;          // which of the 8 groups of 4 scores per 32 use the polynomial exp2 for their second pair (0xAA: every other group = 25 %).  Default 0: at the 1 000 W power cap the extra FMA instructions cost more than the SFU time they save (0x00 10 340, 0x22 10 315, 0xAA 10 270, 0xFF 10 230 events/s on one box)
 constexpr uint32_t kAtt2OffKv = 16384;                                   // after Q
 constexpr uint32_t kAtt2OffP = kAtt2OffKv + kAtt2Stages * 16384;         // 2 x 16 KB
 constexpr uint32_t kAtt2OffBars = kAtt2OffP + 2 * 16384;
