@@ -58,55 +58,66 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
 // four consecutive values of a per-event adaLN row: from the copy staged in shared memory (the usual case) or from global memory
 __device__ __forceinline__ float4 par_f4(bool staged, uint32_t sm_addr, const float* g) { return staged ? lds_f4(sm_addr) : ldg128_stream(g); }
 
-// acc + bias (+ LeakyReLU), gated into the residual: returns the new residual chunk in r[] (as bits)
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) { uint64_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ float sum_f32x2(uint64_t v) { return f32x2_lo(v) + f32x2_hi(v); }
+
+// acc + bias (+ LeakyReLU), gated into the residual: returns the new residual chunk in r[] (as bits).  Everything whose operands
+// already sit in registers runs as packed f32x2 instructions (two columns per FFMA2 / FADD2): at the power cap the epilogue's
+// instruction count is what the chain pays for.  s1 / s2 are PAIRS of partial sums (even / odd columns).
 template <bool kAct>
 __device__ __forceinline__ void chain_resid_chunk(uint32_t (&r)[32], const float (&xr)[32], const float* bias /*constant bank*/,
-                                                  bool staged, uint32_t gate_sm, const float* __restrict__ gate, float& s1, float& s2) {
+                                                  bool staged, uint32_t gate_sm, const float* __restrict__ gate, uint64_t& s1, uint64_t& s2) {
+    const uint64_t slope2 = pack_f32x2(kLeaky, kLeaky);
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
         const float4 g4 = par_f4(staged, gate_sm + j * 4, gate + j);
-        const float bb[4] = {bias[j], bias[j + 1], bias[j + 2], bias[j + 3]}, gg[4] = {g4.x, g4.y, g4.z, g4.w};
+        const uint64_t gg[2] = {pack_f32x2(g4.x, g4.y), pack_f32x2(g4.z, g4.w)};
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            float w = __uint_as_float(r[j + u]) + bb[u];
-            if (kAct) w = leaky_relu(w);
-            w = fmaf(gg[u], w, xr[j + u]);
-            s1 += w; s2 = fmaf(w, w, s2);
-            r[j + u] = __float_as_uint(w);
+        for (int u = 0; u < 2; ++u) {
+            float w0 = __uint_as_float(r[j + 2 * u]) + bias[j + 2 * u], w1 = __uint_as_float(r[j + 2 * u + 1]) + bias[j + 2 * u + 1];
+            uint64_t w = pack_f32x2(w0, w1);
+            if (kAct) { const uint64_t lk = fmul2(w, slope2); w = pack_f32x2(fmaxf(w0, f32x2_lo(lk)), fmaxf(w1, f32x2_hi(lk))); }   // LeakyReLU = max(x, 0.01 x)
+            w = ffma2(gg[u], w, pack_f32x2(xr[j + 2 * u], xr[j + 2 * u + 1]));
+            s1 = fadd2(s1, w); s2 = ffma2(w, w, s2);
+            r[j + 2 * u] = (uint32_t)w; r[j + 2 * u + 1] = (uint32_t)(w >> 32);
         }
     }
 }
 
 // first-layer mode: leaky(acc + bias + per-event bias) IS the residual row (feat_0, models/flow_model.py:224-228)
 __device__ __forceinline__ void chain_first_chunk(uint32_t (&r)[32], const float* bias /*constant bank*/, bool staged, uint32_t rb_sm, const float* __restrict__ rb,
-                                                  float& s1, float& s2) {
+                                                  uint64_t& s1, uint64_t& s2) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
         const float4 b4 = par_f4(staged, rb_sm + j * 4, rb + j);
         const float bb[4] = {bias[j] + b4.x, bias[j + 1] + b4.y, bias[j + 2] + b4.z, bias[j + 3] + b4.w};
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const float w = leaky_relu(__uint_as_float(r[j + u]) + bb[u]);
-            s1 += w; s2 = fmaf(w, w, s2);
-            r[j + u] = __float_as_uint(w);
+        for (int u = 0; u < 4; u += 2) {
+            const float w0 = leaky_relu(__uint_as_float(r[j + u]) + bb[u]), w1 = leaky_relu(__uint_as_float(r[j + u + 1]) + bb[u + 1]);
+            const uint64_t w = pack_f32x2(w0, w1);
+            s1 = fadd2(s1, w); s2 = ffma2(w, w, s2);
+            r[j + u] = __float_as_uint(w0); r[j + u + 1] = __float_as_uint(w1);
         }
     }
 }
 
-// r[] (bits of the residual row chunk) -> (LN(r) * w + b) * (1 + scale) + shift in place; accumulates sum / sum of squares of the result
-__device__ __forceinline__ void chain_ln_mod_chunk(uint32_t (&r)[32], float mean, float rstd, const float* lw, const float* lb /*constant bank*/,
+// r[] (bits of the residual row chunk) -> (LN(r) * w + b) * (1 + scale) + shift in place; accumulates sum / sum of squares of the
+// result as PAIRS of partial sums.  rs2 = (rstd, rstd), nm2 = (-mean rstd, -mean rstd).
+__device__ __forceinline__ void chain_ln_mod_chunk(uint32_t (&r)[32], uint64_t rs2, uint64_t nm2, const float* lw, const float* lb /*constant bank*/,
                                                    bool staged, uint32_t sc_sm, uint32_t sh_sm, const float* __restrict__ sc, const float* __restrict__ sh,
-                                                   float& t1, float& t2) {
+                                                   uint64_t& t1, uint64_t& t2) {
+    const uint64_t one2 = pack_f32x2(1.f, 1.f);
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
         const float4 s4 = par_f4(staged, sc_sm + j * 4, sc + j), h4 = par_f4(staged, sh_sm + j * 4, sh + j);
-        const float ss[4] = {s4.x, s4.y, s4.z, s4.w}, hs[4] = {h4.x, h4.y, h4.z, h4.w};
+        const uint64_t ss[2] = {fadd2(pack_f32x2(s4.x, s4.y), one2), fadd2(pack_f32x2(s4.z, s4.w), one2)}, hs[2] = {pack_f32x2(h4.x, h4.y), pack_f32x2(h4.z, h4.w)};
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            float y = fmaf((__uint_as_float(r[j + u]) - mean) * rstd, lw[j + u], lb[j + u]);
-            y = fmaf(y, 1.f + ss[u], hs[u]);
-            t1 += y; t2 = fmaf(y, y, t2);
-            r[j + u] = __float_as_uint(y);
+        for (int u = 0; u < 2; ++u) {
+            const uint64_t xh = ffma2(pack_f32x2(__uint_as_float(r[j + 2 * u]), __uint_as_float(r[j + 2 * u + 1])), rs2, nm2);
+            const float y0 = fmaf(f32x2_lo(xh), lw[j + 2 * u], lb[j + 2 * u]), y1 = fmaf(f32x2_hi(xh), lw[j + 2 * u + 1], lb[j + 2 * u + 1]);
+            const uint64_t y = ffma2(pack_f32x2(y0, y1), ss[u], hs[u]);
+            t1 = fadd2(t1, y); t2 = ffma2(y, y, t2);
+            r[j + 2 * u] = (uint32_t)y; r[j + 2 * u + 1] = (uint32_t)(y >> 32);
         }
     }
 }
@@ -325,13 +336,13 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                 if (warp == 2 && lane == 0) CHAIN_STAMP(tile_i, 10);
                 tc_fence_after();
                 stage_rows(p.gate_msa, p.scale_mlp, p.shift_mlp, p.ld_mod);
-                float s1 = 0.f, s2 = 0.f;
+                uint64_t s1p = 0ull, s2p = 0ull;
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
                     uint32_t r[32];
                     tmem_ld32(t_col + c * 32, r);
                     tmem_ld_wait();
-                    chain_resid_chunk<false>(r, xr, &p.cst[0][hh * 128 + c * 32], staged, psm + c * 128, p.gate_msa + eo + c * 32, s1, s2);
+                    chain_resid_chunk<false>(r, xr, &p.cst[0][hh * 128 + c * 32], staged, psm + c * 128, p.gate_msa + eo + c * 32, s1p, s2p);
                     if (valid) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 8) stg256_stream(xrow + (c * 4 + (j >> 3)) * 1024, &r[j]);
@@ -344,24 +355,27 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                 }
                 if (warp == 2 && lane == 0) CHAIN_STAMP(tile_i, 22);
                 tmem_st_wait();
+                const float s1 = sum_f32x2(s1p), s2 = sum_f32x2(s2p);
                 sts_f2(st_own, s1, s2);
                 named_bar_sync(1, 256);
                 if (warp == 2 && lane == 0) CHAIN_STAMP(tile_i, 23);
                 const float2 o1 = lds_f2(st_oth);
                 float mean = (s1 + o1.x) * inv_n;
                 float rstd = rsqrtf(fmaxf((s2 + o1.y) * inv_n - mean * mean, 0.f) + kLnEps);
-                float t1 = 0.f, t2 = 0.f;
+                const uint64_t rs2 = pack_f32x2(rstd, rstd), nm2 = pack_f32x2(-mean * rstd, -mean * rstd);
+                uint64_t t1p = 0ull, t2p = 0ull;
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {                            // affine + adaLN modulate, parked back in TMEM
                     uint32_t r[32];
                     tmem_ld32(t_col + c * 32, r);
                     tmem_ld_wait();
-                    chain_ln_mod_chunk(r, mean, rstd, &p.cst[6][hh * 128 + c * 32], &p.cst[7][hh * 128 + c * 32], staged, psm + 1024 + c * 128, psm + 2048 + c * 128,
-                                       p.scale_mlp + eo + c * 32, p.shift_mlp + eo + c * 32, t1, t2);
+                    chain_ln_mod_chunk(r, rs2, nm2, &p.cst[6][hh * 128 + c * 32], &p.cst[7][hh * 128 + c * 32], staged, psm + 1024 + c * 128, psm + 2048 + c * 128,
+                                       p.scale_mlp + eo + c * 32, p.shift_mlp + eo + c * 32, t1p, t2p);
                     tmem_st32(t_col + c * 32, r);
                 }
                 if (warp == 2 && lane == 0) CHAIN_STAMP(tile_i, 24);
                 tmem_st_wait();
+                const float t1 = sum_f32x2(t1p), t2 = sum_f32x2(t2p);
                 sts_f2(st_own + 2048, t1, t2);
                 named_bar_sync(1, 256);
                 const float2 o2 = lds_f2(st_oth + 2048);
@@ -417,14 +431,14 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                 // last layer: the A buffer is handed back to the producer (a_free) as soon as this stage's MMAs retire, so nothing may be staged in it
                 const bool st2 = staged && next;
                 if (st2) stage_rows(kFirst ? p.row_bias : p.gate_mlp, p.scale_nxt, p.shift_nxt, kFirst ? p.ld_row_bias : p.ld_mod);
-                float s1 = 0.f, s2 = 0.f;
+                uint64_t s1p = 0ull, s2p = 0ull;
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
                     uint32_t r[32];
                     tmem_ld32(t_col + c * 32, r);
                     tmem_ld_wait();
-                    if (kFirst) chain_first_chunk(r, &p.cst[2][hh * 128 + c * 32], st2, psm + c * 128, p.row_bias + (size_t)evt * p.ld_row_bias + hh * 128 + c * 32, s1, s2);
-                    else chain_resid_chunk<true>(r, xr, &p.cst[2][hh * 128 + c * 32], st2, psm + c * 128, p.gate_mlp + eo + c * 32, s1, s2);
+                    if (kFirst) chain_first_chunk(r, &p.cst[2][hh * 128 + c * 32], st2, psm + c * 128, p.row_bias + (size_t)evt * p.ld_row_bias + hh * 128 + c * 32, s1p, s2p);
+                    else chain_resid_chunk<true>(r, xr, &p.cst[2][hh * 128 + c * 32], st2, psm + c * 128, p.gate_mlp + eo + c * 32, s1p, s2p);
                     if (valid) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 8) stg256_stream(xrow + (c * 4 + (j >> 3)) * 1024, &r[j]);
@@ -437,19 +451,21 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                 }
                 if (next) {
                     tmem_st_wait();
+                    const float s1 = sum_f32x2(s1p), s2 = sum_f32x2(s2p);
                     sts_f2(st_own, s1, s2);
                     named_bar_sync(1, 256);
                     const float2 o1 = lds_f2(st_oth);
                     const float mean = (s1 + o1.x) * inv_n;
                     const float rstd = rsqrtf(fmaxf((s2 + o1.y) * inv_n - mean * mean, 0.f) + kLnEps);
-                    float t1 = 0.f, t2 = 0.f;
+                    const uint64_t rs2 = pack_f32x2(rstd, rstd), nm2 = pack_f32x2(-mean * rstd, -mean * rstd);
+                    uint64_t t1p = 0ull, t2p = 0ull;
 #pragma unroll 1
                     for (int c = 0; c < 4; ++c) {                        // next layer's LN1 affine + modulate, parked in TMEM (the staged rows are still being read)
                         uint32_t r[32];
                         tmem_ld32(t_col + c * 32, r);
                         tmem_ld_wait();
-                        chain_ln_mod_chunk(r, mean, rstd, &p.cst[8][hh * 128 + c * 32], &p.cst[9][hh * 128 + c * 32], staged, psm + 1024 + c * 128, psm + 2048 + c * 128,
-                                           p.scale_nxt + eo + c * 32, p.shift_nxt + eo + c * 32, t1, t2);
+                        chain_ln_mod_chunk(r, rs2, nm2, &p.cst[8][hh * 128 + c * 32], &p.cst[9][hh * 128 + c * 32], staged, psm + 1024 + c * 128, psm + 2048 + c * 128,
+                                           p.scale_nxt + eo + c * 32, p.shift_nxt + eo + c * 32, t1p, t2p);
                         tmem_st32(t_col + c * 32, r);
                     }
                     tmem_st_wait();
