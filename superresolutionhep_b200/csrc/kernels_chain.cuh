@@ -383,6 +383,7 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                 rstd = rsqrtf(fmaxf((t2 + o2.y) * inv_n - mean * mean, 0.f) + kLnEps);
                 named_bar_sync(1, 256);                                  // every thread has read its partner's sums and the staged rows: the buffer may be overwritten
                 if (warp == 2 && lane == 0) CHAIN_STAMP(tile_i, 25);
+                const uint64_t rs2c = pack_f32x2(rstd, rstd), nm2c = pack_f32x2(-mean * rstd, -mean * rstd);
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {                            // the Dense's own non-affine LayerNorm (models/dense.py:62) -> A
                     uint32_t r[32];
@@ -390,7 +391,10 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                     tmem_ld_wait();
                     float v[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = (__uint_as_float(r[j]) - mean) * rstd;
+                    for (int j = 0; j < 32; j += 2) {
+                        const uint64_t xh = ffma2(pack_f32x2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), rs2c, nm2c);
+                        v[j] = f32x2_lo(xh); v[j + 1] = f32x2_hi(xh);
+                    }
                     chain_store_a(a_sh, rt, hh * 128 + c * 32, v, fp16);
                 }
                 stage_done(true);
