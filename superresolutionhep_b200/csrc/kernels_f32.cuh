@@ -735,11 +735,33 @@ __global__ void __launch_bounds__(256) head_prep_v4_kernel(HeadPrepParams p, Out
         else { __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w); w.x = *reinterpret_cast<uint32_t*>(&a); w.y = *reinterpret_cast<uint32_t*>(&b); }
         *reinterpret_cast<uint2*>(q) = w;
     };
-    auto sum4 = [](float4 v) { return (v.x + v.y) + (v.z + v.w); };
-    auto sq4 = [](float4 v, float m) { const float a = v.x - m, b = v.y - m, c = v.z - m, d = v.w - m; return (a * a + b * b) + (c * c + d * d); };
-    auto aff4 = [](float4 v, float m, float r, float4 w, float4 b) { return make_float4(fmaf((v.x - m) * r, w.x, b.x), fmaf((v.y - m) * r, w.y, b.y), fmaf((v.z - m) * r, w.z, b.z), fmaf((v.w - m) * r, w.w, b.w)); };
-    auto mod4 = [](float4 v, float4 sc, float4 sh) { return make_float4(fmaf(v.x, 1.f + sc.x, sh.x), fmaf(v.y, 1.f + sc.y, sh.y), fmaf(v.z, 1.f + sc.z, sh.z), fmaf(v.w, 1.f + sc.w, sh.w)); };
-    auto nrm4 = [](float4 v, float m, float r) { return make_float4((v.x - m) * r, (v.y - m) * r, (v.z - m) * r, (v.w - m) * r); };
+    // packed f32x2 arithmetic (two columns per instruction): at the power cap the instruction count is what this kernel pays for
+    auto P2 = [](float lo, float hi) { return (uint64_t)__float_as_uint(lo) | ((uint64_t)__float_as_uint(hi) << 32); };
+    auto LO = [](uint64_t v) { return __uint_as_float((uint32_t)v); };
+    auto HI = [](uint64_t v) { return __uint_as_float((uint32_t)(v >> 32)); };
+    auto fma2 = [](uint64_t a, uint64_t b, uint64_t c) { uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; };
+    auto add2 = [](uint64_t a, uint64_t b) { uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; };
+    auto sum4 = [&](float4 v) { const uint64_t t = add2(P2(v.x, v.y), P2(v.z, v.w)); return LO(t) + HI(t); };
+    auto sq4 = [&](float4 v, float m) {                      // sum of (v - m)^2
+        const uint64_t nm = P2(-m, -m), d0 = add2(P2(v.x, v.y), nm), d1 = add2(P2(v.z, v.w), nm);
+        const uint64_t q = fma2(d1, d1, fma2(d0, d0, 0ull));
+        return LO(q) + HI(q);
+    };
+    auto aff4 = [&](float4 v, float m, float r, float4 w, float4 b) {      // ((v - m) r) w + b, with (v - m) r as one FMA: v r - m r
+        const uint64_t rr = P2(r, r), nm = P2(-m * r, -m * r);
+        const uint64_t y0 = fma2(fma2(P2(v.x, v.y), rr, nm), P2(w.x, w.y), P2(b.x, b.y)), y1 = fma2(fma2(P2(v.z, v.w), rr, nm), P2(w.z, w.w), P2(b.z, b.w));
+        return make_float4(LO(y0), HI(y0), LO(y1), HI(y1));
+    };
+    auto mod4 = [&](float4 v, float4 sc1p /* 1 + scale */, float4 sh) {
+        const uint64_t y0 = fma2(P2(v.x, v.y), P2(sc1p.x, sc1p.y), P2(sh.x, sh.y)), y1 = fma2(P2(v.z, v.w), P2(sc1p.z, sc1p.w), P2(sh.z, sh.w));
+        return make_float4(LO(y0), HI(y0), LO(y1), HI(y1));
+    };
+    auto nrm4 = [&](float4 v, float m, float r) {
+        const uint64_t rr = P2(r, r), nm = P2(-m * r, -m * r);
+        const uint64_t y0 = fma2(P2(v.x, v.y), rr, nm), y1 = fma2(P2(v.z, v.w), rr, nm);
+        return make_float4(LO(y0), HI(y0), LO(y1), HI(y1));
+    };
+    auto plus1 = [](float4 v) { return make_float4(1.f + v.x, 1.f + v.y, 1.f + v.z, 1.f + v.w); };
     const int c0 = lane * 4, c1 = 128 + lane * 4;
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     const float4 fw0 = ld4(p.fn_w + c0), fw1 = ld4(p.fn_w + c1), fb0 = ld4(p.fn_b + c0), fb1 = ld4(p.fn_b + c1);
@@ -770,8 +792,8 @@ __global__ void __launch_bounds__(256) head_prep_v4_kernel(HeadPrepParams p, Out
             const float* cx = p.ctx + (size_t)ev * 160;
             x0 = ld4(cx + c0); x1 = hx1 ? ld4(cx + c1) : z4;
             const float* sh = p.shift + (size_t)ev * p.ld_mod; const float* sc = p.scale + (size_t)ev * p.ld_mod;
-            sc0 = ld4(sc + c0); sc1 = ld4(sc + c1); sh0 = ld4(sh + c0); sh1 = ld4(sh + c1);
-            if (hc) { scc = ld4(sc + 256 + c0); shc = ld4(sh + 256 + c0); }
+            sc0 = plus1(ld4(sc + c0)); sc1 = plus1(ld4(sc + c1)); sh0 = ld4(sh + c0); sh1 = ld4(sh + c1);       // sc* hold 1 + scale
+            if (hc) { scc = plus1(ld4(sc + 256 + c0)); shc = ld4(sh + 256 + c0); }
             ev_prev = ev;
         }
         // final_norm over h = 256
