@@ -334,7 +334,7 @@ void launch_chain_first(Engine& E, int M, const int* rev) {
 void bf16_forward(Engine& E, const Pass& p, const int* rev, const StageRef& st) {
     SrhepHandle* h = E.h;
     const SrhepDims& d = h->d; const Layout& L = h->L; Bf16Weights& bw = h->bw;
-    const int M = p.r1 - p.r0, H = d.h_dim, ncol = d.cond + d.noisy_out;
+    const int M = p.r1 - p.r0, H = d.h_dim;
     const int fp16 = h->precision == SRHEP_PREC_FP16;
     float* x = h->xres;
     const float* mod = h->mod;

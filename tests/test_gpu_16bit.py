@@ -104,10 +104,32 @@ def test_tensor_core_attention_matches_simt_attention():
         del os.environ["SRHEP_ATTN_SIMT"]
     scale = float(v_simt.abs().max())
     print(f"tc vs simt attention: max|diff| {float((v_tc - v_simt).abs().max()):.3e} of {scale:.3f}")
-    # P is rounded to bf16 before P.V on the tensor-core path (fp32 on the SIMT path) and a quarter of the exponentials use the cubic
-    # exp2; both runs carry independent bf16 noise through six layers, so the bf16 single-evaluation bound (3e-2 of max|ref|)
+    # P is rounded to bf16 before P.V on the tensor-core path (fp32 on the SIMT path); both runs carry independent bf16 noise through six layers, so the bf16 single-evaluation bound (3e-2 of max|ref|)
     # applies to their difference; the fp16 operand mode is held to 1e-2 against the fp32 oracle in test_velocity_matches_oracle.
     torch.testing.assert_close(v_tc, v_simt, rtol=3e-2, atol=3e-2 * scale)
+
+
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+def test_first_layer_chain_mode_matches_the_two_gemm_path(precision):
+    """feat_0 -> LN1.modulate -> layer-0 q|k|v runs as ONE launch of the chain kernel (first-layer mode); SRHEP_NO_CHAIN_FIRST=1
+    selects the two tcgen05 GEMM launches it replaced.  Same operands and the same fp32 epilogue math in a different
+    reduction order: the velocities must agree far inside the 16-bit tolerance (ragged row count, events across tile edges)."""
+    m, sd, dims = make_model("single_e", 13, precision)
+    counts = np.array([124, 132, 4, 256, 804, 60, 388])
+    batch = synthetic_events("single_e", len(counts), seed=21, counts=counts)
+    x = synthetic_noise(batch, seed=22)
+    t = torch.full((len(counts),), 0.3)
+    mask = batch["q_mask"]
+    v_fused = m(to_dev(batch), x.cuda(), t.cuda()).cpu()[mask]
+    os.environ["SRHEP_NO_CHAIN_FIRST"] = "1"
+    try:
+        v_two = m(to_dev(batch), x.cuda(), t.cuda()).cpu()[mask]
+    finally:
+        del os.environ["SRHEP_NO_CHAIN_FIRST"]
+    scale = float(v_two.abs().max())
+    print(f"[{precision}] first-layer chain vs two GEMMs: max|diff| {float((v_fused - v_two).abs().max()):.3e} of {scale:.3f}")
+    assert torch.isfinite(v_fused).all()
+    torch.testing.assert_close(v_fused, v_two, rtol=5e-3, atol=5e-3 * scale)
 
 
 @pytest.mark.parametrize("precision", ["fp16", "bf16"])
