@@ -111,9 +111,12 @@ int srhep_sample(SrhepHandle* h, const float* x0_dev, const float* t_grid_host, 
                  int32_t method, int32_t ret_seq, float* x_seq_dev, int32_t* nfe_out, void* stream);
 
 /* Adaptive dopri5 with the step controller of torchdiffeq (atol/rtol as at
- * models/flow_model.py:321-323); rms norms are taken over real cells only. Host-synchronous
- * (one scalar read back per attempted step, like the reference).  stats_out (host, 3 ints,
- * may be NULL): nfe, accepted, rejected. */
+ * models/flow_model.py:321-323; the reference's default method, :303); rms norms are taken over
+ * real cells only.  Device-resident: t, dt, accept/reject and the output-grid cursor live in
+ * device memory and the adaptive loop is a conditional WHILE node of one CUDA graph, so the
+ * call launches once and synchronises once, at its end, to return the statistics (with
+ * srhep_set_use_graph(h, 0) the loop is driven from the host, one scalar read back per attempted
+ * step like torchdiffeq).  stats_out (host, 3 ints, may be NULL): nfe, accepted, rejected. */
 int srhep_sample_dopri5(SrhepHandle* h, const float* x0_dev, const float* t_grid_host, int32_t n_steps,
                         float atol, float rtol, int32_t ret_seq, float* x_seq_dev,
                         int32_t* stats_out, void* stream);

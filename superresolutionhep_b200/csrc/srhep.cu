@@ -22,6 +22,7 @@
 #include "kernels_head.cuh"
 #include "kernels_attn.cuh"
 #include "kernels_embed.cuh"
+#include "kernels_ode.cuh"
 
 using namespace srhep;
 
@@ -148,6 +149,13 @@ struct SrhepHandle {
     int* stage_idx_dev = nullptr; size_t cap_stage_idx = 0;
     cudaEvent_t sp_done = nullptr;
     cudaStream_t cap_stream = nullptr;
+
+    // device-resident dopri5 (dopri5.inl): control block, per-pass stage descriptors and cursors, time grid, the cached graph
+    Dopri5Ctl* dp_ctl = nullptr; Dopri5Ctl* dp_ctl_host = nullptr;
+    StageParams* dp_sp = nullptr; int* dp_idx = nullptr; size_t dp_cap_pass = 0;
+    float* dp_tg = nullptr; size_t dp_cap_tg = 0;
+    cudaGraphExec_t dp_exec = nullptr; cudaStream_t dp_body_stream = nullptr;
+    int dp_init_nodes = 0, dp_body_nodes = 0;
 
     // debug taps (single pass)
     float* tap_layers = nullptr; float* tap_feat0 = nullptr; float* tap_final = nullptr; size_t cap_tap = 0;
@@ -568,6 +576,7 @@ int alloc_workspace(SrhepHandle* h) {
 
 void drop_graphs(SrhepHandle* h) {
     for (auto& p : h->passes) if (p.exec) { cudaGraphExecDestroy(p.exec); p.exec = nullptr; }
+    if (h->dp_exec) { cudaGraphExecDestroy(h->dp_exec); h->dp_exec = nullptr; }
 }
 
 int ensure_state(SrhepHandle* h, bool need_k) {
@@ -647,6 +656,8 @@ int eval_all(SrhepHandle* h, cudaStream_t s, const float* x, float t, const floa
     }
     return 0;
 }
+
+#include "dopri5.inl"
 
 }  // namespace
 
@@ -763,6 +774,9 @@ int srhep_destroy(SrhepHandle* h) {
     for (void* p : ptrs) if (p) cudaFree(p);
     for (float* p : h->kbuf) if (p) cudaFree(p);
     bf16_free_weights(h);
+    for (void* p : {(void*)h->dp_ctl, (void*)h->dp_sp, (void*)h->dp_idx, (void*)h->dp_tg}) if (p) cudaFree(p);
+    if (h->dp_ctl_host) cudaFreeHost(h->dp_ctl_host);
+    if (h->dp_body_stream) cudaStreamDestroy(h->dp_body_stream);
     if (h->sp_host) cudaFreeHost(h->sp_host);
     if (h->red_host) cudaFreeHost(h->red_host);
     if (h->sp_done) cudaEventDestroy(h->sp_done);
@@ -993,9 +1007,9 @@ int srhep_sample(SrhepHandle* h, const float* x0, const float* tg, int32_t n_ste
 
 
 // torchdiffeq's adaptive dopri5 (RKAdaptiveStepsizeODESolver with the Dormand-Prince tableau,
-// restated in oracle/odeint.py and SURVEY Appendix C).  Host-synchronous: one scalar is read
-// back per attempted step, as in the reference.  Norms run over real cells only (the
-// reference's include the padded slots, SURVEY 7 "Solver semantics").
+// restated in oracle/odeint.py and SURVEY Appendix C).  Device-resident by default (dopri5.inl,
+// kernels_ode.cuh); the host-driven loop below is the use_graph = 0 variant.  Norms run over real
+// cells only (the reference's include the padded slots, SURVEY 7 "Solver semantics").
 int srhep_sample_dopri5(SrhepHandle* h, const float* x0, const float* tg, int32_t n_steps, float atol, float rtol,
                         int32_t ret_seq, float* x_seq, int32_t* stats_out, void* stream) {
     if (!h) return SRHEP_E_INVALID;
@@ -1011,11 +1025,15 @@ int srhep_sample_dopri5(SrhepHandle* h, const float* x0, const float* tg, int32_
     CK(h, cudaSetDevice(h->device));
     cudaStream_t s = (cudaStream_t)stream;
     int rc;
-    if ((rc = ensure_state(h, true))) return rc;
-    Engine E{h, s};
     auto out_ptr = [&](int j) -> float* { return ret_seq ? x_seq + (size_t)j * T : x_seq; };
     if (ret_seq || n_steps == 1) { if (out_ptr(0) != x0) CK(h, cudaMemcpyAsync(out_ptr(0), x0, T * sizeof(float), cudaMemcpyDeviceToDevice, s)); }
     if (n_steps == 1) return SRHEP_OK;
+    // Production: the whole adaptive loop runs on the device (one graph launch, no host round trip per step).  With graphs
+    // switched off (srhep_set_use_graph(h, 0): diagnostics, A/B tests) the same arithmetic is driven from the host below,
+    // which reads one scalar back per attempted step like the reference's torchdiffeq loop.
+    if (h->use_graph) return dopri5_device(h, x0, tg, n_steps, atol, rtol, ret_seq, x_seq, stats_out, s);
+    if ((rc = ensure_state(h, true))) return rc;
+    Engine E{h, s};
 
     static const double alpha[6] = {1 / 5., 3 / 10., 4 / 5., 8 / 9., 1., 1.};
     static const double beta[6][6] = {

@@ -19,8 +19,8 @@ What is different, and why:
   branch, keyed ``"<Tree>/<branch>"``.  Neither package is installable in the build image, so only the fall-back is tested;
 * keys that the shipped single_e YAMLs do not define but the reference reads (``store_ensemble_components``,
   ``store_energy_incidence``, ``max_particles``: SURVEY.md Appendix D) default to False / False / 4 instead of raising;
-* ``-p/--precision`` selects the arithmetic of the sm_100a path: ``highest`` = fp32 kernels, ``high`` / ``medium`` = bf16
-  tcgen05 operands (the reference passes the same string to ``torch.set_float32_matmul_precision``, inference.py:346,374).
+* ``-p/--precision`` selects the arithmetic of the sm_100a path: ``highest`` = fp32 kernels, ``high`` / ``medium`` = fp16
+  tcgen05 operands with fp32 accumulation (the reference passes the same string to ``torch.set_float32_matmul_precision``, inference.py:346,374).
 """
 from __future__ import annotations
 
@@ -145,6 +145,17 @@ class Inference:
                 if key in batch:
                     v = batch[key].reshape(lm.shape)[lm.to(batch[key].device)]
                     self._append_packed(self.low_dict_to_zip, out, v * unit if unit != 1.0 else v, lcounts)
+        if self.store_incidence:                                               # inference.py:266-273: per-particle energy incidence, zero rows up to max_particles
+            if "low_e_part_0" not in batch or "high_e_part_0" not in batch or "particle_pt" not in batch:
+                raise KeyError("store_energy_incidence needs low_e_part_i / high_e_part_i / particle_pt in the batch (collate_graphs_plus)")
+            npy = lambda v: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v))
+            sq = lambda a: a.squeeze(-1) if a.ndim and a.shape[-1] == 1 else a
+            for bs_i in range(mask.shape[0]):
+                n_part = len(batch["particle_pt"][bs_i])
+                for pi in range(self.max_particles):
+                    for tree, pre in ((self.low_dict_to_zip, "low"), (hd, "high")):
+                        src = npy(batch[f"{pre}_e_part_{pi}"][bs_i]) if pi < n_part else np.zeros_like(npy(batch[f"{pre}_e_part_0"][bs_i]))
+                        tree[f"e_part_{pi}"].append(sq(src))
         for k in PARTICLE_KEYS:
             if k in batch:
                 self.particle_dict_to_zip[k].extend(np.asarray(p.detach().cpu().numpy() if torch.is_tensor(p) else p) for p in batch[k])
@@ -236,7 +247,7 @@ def main(argv=None):
     with open(args.inference_path) as fp:
         inference_cfg = yaml.safe_load(fp)
     inf_dicts = expand_inf_dicts(inference_cfg, args)
-    torch.set_float32_matmul_precision(args.precision)                      # read by FlowModel: highest -> fp32 kernels, else bf16 tcgen05
+    torch.set_float32_matmul_precision(args.precision)                      # read by FlowModel: highest -> fp32 kernels, else fp16 tcgen05 operands
     if str(inference_cfg.get("gpu", -1)) not in ("-1", "None"):
         os.environ["CUDA_VISIBLE_DEVICES"] = str(inference_cfg["gpu"])
     inf_obj = Inference(inference_cfg)

@@ -22,6 +22,9 @@ from . import _lib
 from .pflow import _var_transform_c
 
 
+SR_KEYS = ("eta", "cosphi", "sinphi", "e_proxy", "layer", "q_mask")          # the collate keys FlowModel.forward reads
+
+
 def stored_steps(n_steps: int, n_steps_to_store: int):
     """inference.py:54-69: grid points of ``linspace(0, 1, n_steps)`` nearest to ``linspace(0, 1, n_store + 1)``
     (last one dropped) -> (times, indices)."""
@@ -79,12 +82,23 @@ def ensemble_sample(model, batch: Dict[str, torch.Tensor], target_cfg, n_ensembl
     mask = batch["q_mask"].to(dev).bool()
     B, N = mask.shape
     E = int(n_ensemble)
-    rep = {}
-    for k, v in batch.items():
-        rep[k] = v.to(dev).repeat(E, *([1] * (v.dim() - 1))) if torch.is_tensor(v) else v
     if x0 is None:
         x0 = torch.randn(E, B, N, 1, device=dev)
-    xs = model.generate_samples(rep, n_steps=n_steps, method=method, ret_seq=True, x0=x0.reshape(E * B, N, 1).to(dev))     # (n_steps, E*B, N, 1)
+    x0 = x0.to(dev).reshape(E, B, N, 1)
+    # only what FlowModel.forward reads travels (flow_model.py:187-189): collate_graphs also emits edge_mask (B x Nmax^2
+    # bytes, never used) and the low_* / target / raw tensors, which must not be tiled E times
+    cond = {k: batch[k].to(dev) for k in SR_KEYS}
+    cond["q_mask"] = mask
+    if method == "dopri5":
+        # the reference draws the members in E separate odeint calls (inference.py:146-149): an adaptive solver shares ONE
+        # step sequence and error norm across its batch, so the members stay separate calls here too (same binding reused)
+        cond["edge_mask"] = None
+        xs = torch.stack([model.generate_samples(cond, n_steps=n_steps, method=method, ret_seq=True, x0=x0[i]) for i in range(E)], 1)
+        xs = xs.reshape(n_steps, E * B, N, 1)
+    else:
+        rep = {k: v.repeat(E, *([1] * (v.dim() - 1))) for k, v in cond.items()}
+        rep["edge_mask"] = None
+        xs = model.generate_samples(rep, n_steps=n_steps, method=method, ret_seq=True, x0=x0.reshape(E * B, N, 1))     # (n_steps, E*B, N, 1)
     ts, idx = stored_steps(n_steps, n_steps_to_store)
     keep = idx + [n_steps - 1]
     sel = xs[keep][..., 0].reshape(len(keep), E, B, N)[..., mask]                       # (S, E, T)

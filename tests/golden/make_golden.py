@@ -7,7 +7,9 @@ Needs /root/reference (read-only mount).  The velocity network is the reference'
 oracle/odeint.py (torchdiffeq is not installable, see its header).  Weights come from
 ``synthetic_state_dict`` (seeded) because the SR checkpoints are missing from the mount.
 Outputs (committed): tests/golden/sr_taps_single_e.pt, sr_taps_multipart.pt,
-sr_config1_single_e.pt, sr_dopri5_single_e.pt.
+sr_config1_single_e.pt, sr_dopri5_single_e.pt, sr_traj_multipart.pt.
+
+    python tests/golden/make_golden.py [case ...]      # taps | dopri5 | config1 | multipart (default: all)
 """
 import os
 import sys
@@ -109,9 +111,58 @@ def dopri5_case(fname, n_events=6, n_steps=5):
                os.path.join(OUT, fname))
 
 
+MULTIPART_COUNTS = [3280, 2048, 1600, 1312, 960, 800, 640, 640, 480, 400, 320, 256, 128, 48, 16, 16]
+
+
+def multipart_case(fname, counts=MULTIPART_COUNTS, n_steps=25, group=4):
+    """BASELINE.json configs[2] shapes: 16 multipart events from 16 cells up to the maximum of 3280, Euler + midpoint
+    trajectories with n_steps = 25.  Events are independent under a fixed grid, so the reference model is run on groups of
+    `group` events of similar length (padding all 16 to 3280 cells would cost 4x the time for the same real rows); the
+    noise of event i is row i of ONE seeded (B, Nmax, 1) draw, so a single-batch run of the product sees the same x0.
+    Stored packed (real cells only, entry order)."""
+    m = ref_model("multipart")
+    counts = np.asarray(counts)
+    batch = synthetic_events("multipart", len(counts), seed=4242, counts=counts)
+    x0 = synthetic_noise(batch, seed=17)
+    mask = batch["q_mask"]
+    out = {"config": "multipart", "weight_seed": WEIGHT_SEED, "event_seed": 4242, "noise_seed": 17, "counts": [int(c) for c in counts],
+           "n_steps": n_steps}
+    for method in ("euler", "midpoint"):
+        finals, mids, v0s, nfe = [], [], [], 0
+        t0 = time.time()
+        for a in range(0, len(counts), group):
+            b = min(a + group, len(counts))
+            nmax = int(counts[a:b].max())
+            sub = {k: (v[a:b, :nmax].contiguous() if torch.is_tensor(v) else v) for k, v in batch.items()}
+            xs0 = x0[a:b, :nmax].contiguous()
+            rec = []
+
+            def f(t, x, sub=sub, rec=rec):
+                v = m(sub, x, t * torch.ones(x.shape[0]))
+                if not rec:
+                    rec.append(v.clone())
+                rec.append(None)
+                return v
+            with torch.no_grad():
+                xs = odeint(f, xs0, torch.linspace(0, 1, n_steps), method=method)
+            sm = sub["q_mask"]
+            finals.append(xs[-1][sm][:, 0]); mids.append(xs[n_steps // 2][sm][:, 0]); v0s.append(rec[0][sm][:, 0])
+            nfe = len(rec) - 1
+            print(method, f"events {a}:{b} nmax {nmax} {time.time()-t0:.0f}s", flush=True)
+        out[method] = {"x_final": torch.cat(finals), "x_mid": torch.cat(mids), "v0": torch.cat(v0s), "nfe": nfe}
+    assert out["euler"]["x_final"].numel() == int(mask.sum())
+    torch.save(out, os.path.join(OUT, fname))
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
-    taps_case("single_e", [12, 40, 24], 48, "sr_taps_single_e.pt")
-    taps_case("multipart", [16, 80, 48, 32], 96, "sr_taps_multipart.pt")
-    dopri5_case("sr_dopri5_single_e.pt")
-    config1_case("sr_config1_single_e.pt")
+    cases = sys.argv[1:] or ["taps", "dopri5", "config1", "multipart"]
+    if "taps" in cases:
+        taps_case("single_e", [12, 40, 24], 48, "sr_taps_single_e.pt")
+        taps_case("multipart", [16, 80, 48, 32], 96, "sr_taps_multipart.pt")
+    if "dopri5" in cases:
+        dopri5_case("sr_dopri5_single_e.pt")
+    if "config1" in cases:
+        config1_case("sr_config1_single_e.pt")
+    if "multipart" in cases:
+        multipart_case("sr_traj_multipart.pt")

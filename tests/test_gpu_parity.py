@@ -90,6 +90,23 @@ def test_config1_trajectory_matches_golden(method, golden_dir):
     assert torch.equal(xl.cpu()[mask], xs[-1].cpu()[mask])
 
 
+@pytest.mark.parametrize("method", ["euler", "midpoint"])
+def test_multipart_trajectory_matches_golden(method, golden_dir):
+    """BASELINE.json configs[2] shapes, fp32 path: 16 multipart events (16 ... 3280 cells) as one batch against the
+    reference's own trajectories (tests/golden/make_golden.py multipart)."""
+    g = torch.load(os.path.join(golden_dir, "sr_traj_multipart.pt"))
+    m, sd, dims = make_model("multipart", g["weight_seed"])
+    batch = synthetic_events("multipart", len(g["counts"]), seed=g["event_seed"], counts=np.array(g["counts"]))
+    x0 = synthetic_noise(batch, seed=g["noise_seed"])
+    mask = batch["q_mask"]
+    xs = m.generate_samples(to_dev(batch), n_steps=g["n_steps"], method=method, ret_seq=True, x0=x0.cuda()).cpu()
+    assert m.last_stats["nfe"] == g[method]["nfe"]
+    close(xs[-1][mask][:, 0], g[method]["x_final"], 1e-4, 1e-4, "x_final")
+    close(xs[g["n_steps"] // 2][mask][:, 0], g[method]["x_mid"], 1e-4, 1e-4, "x_mid")
+    v0 = m(to_dev(batch), x0.cuda(), torch.zeros(len(g["counts"])).cuda()).cpu()
+    close(v0[mask][:, 0], g[method]["v0"], 1e-4, 2e-5, "v(t=0)")
+
+
 def test_dopri5_matches_golden(golden_dir):
     """Adaptive solver: both sides integrate the same ODE to atol = rtol = 1e-4; the step
     sequences differ (the reference's error norm includes padded slots), so the comparison
@@ -104,6 +121,37 @@ def test_dopri5_matches_golden(golden_dir):
     assert st["nfe"] == 2 + 6 * (st["accepted"] + st["rejected"])
     for j in range(g["n_steps"]):
         close(xs[j].cpu()[mask], g["x_seq"][j][mask], 2e-3, 2e-3, f"x_seq[{j}]")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_device_resident_dopri5_equals_host_driven_loop(precision):
+    """The adaptive loop as one conditional CUDA graph (controller, accept / reject, dense output on the device; no host
+    round trip per step) against the same arithmetic driven from the host (use_graph = False, one scalar read back per
+    attempted step): same accepted / rejected step sequence, same outputs up to the controller's libm-vs-device `pow`
+    and FMA contraction of the interpolation coefficients.  Multi-pass bindings and ret_seq = False included."""
+    m, sd, dims = make_model("single_e", 19, precision)
+    counts = np.array([124, 8, 132, 256, 64, 300])
+    batch = synthetic_events("single_e", len(counts), seed=31, counts=counts)
+    x0 = synthetic_noise(batch, seed=32)
+    mask = batch["q_mask"]
+    db = to_dev(batch)
+    dev = m.generate_samples(db, n_steps=6, method="dopri5", ret_seq=True, x0=x0.cuda()).cpu()
+    st_dev = dict(m.last_stats)
+    again = m.generate_samples(db, n_steps=6, method="dopri5", ret_seq=True, x0=x0.cuda()).cpu()       # cached graph, second launch
+    assert torch.equal(again[:, mask], dev[:, mask]) or precision == "fp32"                            # (double atomics order the norm sums freely: last-bit dt differences are allowed)
+    last = m.generate_samples(db, n_steps=6, method="dopri5", ret_seq=False, x0=x0.cuda()).cpu()
+    close(last[mask], dev[-1][mask], 1e-5, 1e-5, "ret_seq=False")
+    m.pass_tokens = 300                                                                                # several passes inside the graph body
+    cut = m.generate_samples(db, n_steps=6, method="dopri5", ret_seq=True, x0=x0.cuda()).cpu()
+    close(cut[:, mask], dev[:, mask], 1e-5, 1e-5, "multi-pass")
+    m.pass_tokens = 0
+    m.use_graph = False
+    host = m.generate_samples(db, n_steps=6, method="dopri5", ret_seq=True, x0=x0.cuda()).cpu()
+    st_host = dict(m.last_stats)
+    print(f"[{precision}] device {st_dev} host {st_host}")
+    assert st_dev == st_host and st_dev["nfe"] == 2 + 6 * (st_dev["accepted"] + st_dev["rejected"])
+    assert torch.equal(dev[0], x0)
+    close(dev[:, mask], host[:, mask], 1e-5, 1e-5, "device vs host dopri5")
 
 
 # ------------------------------------------------------------------------------------ oracle

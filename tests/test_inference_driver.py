@@ -86,3 +86,28 @@ def test_end_to_end_from_checkpoint_to_trees(tmp_path):
     assert "High_Tree/e_pred_raw" in z.files and len(z["High_Tree/e_pred_raw"]) == 5 and z["High_Tree/e_pred_raw"][3].shape == (64,)
     with pytest.raises(RuntimeError, match="dataset.py"):
         obj.get_dataloader({"truth_path": "x.root", "n_events": 1, "entry_start": 0, "batch_size": 1, "num_workers": 0})
+
+
+def test_energy_incidence_branches_are_filled_and_zero_padded():
+    """inference.py:266-273: ``e_part_i`` of Low_Tree / High_Tree come from ``low_e_part_i`` / ``high_e_part_i`` for the event's
+    particles and are zero arrays (shaped like particle 0's) up to ``max_particles``."""
+    obj = inf.Inference.__new__(inf.Inference)
+    obj.ts_to_store, obj.ts_to_store_idx, obj.target_cfg = [], [], TARGET
+    obj.prep_dicts({"n_ensemble": 1, "store_energy_incidence": True, "max_particles": 3})
+    counts = np.array([8, 4])
+    b = synthetic_events("single_e", 2, seed=3, counts=counts)
+    b["low_q_mask"] = torch.tensor([[True, True], [True, False]])
+    b["particle_pt"] = [torch.rand(2), torch.rand(1)]
+    for pi in range(2):
+        b[f"low_e_part_{pi}"] = [torch.rand(2, 1) + pi, torch.rand(1, 1) + pi]
+        b[f"high_e_part_{pi}"] = [torch.rand(8, 1) + pi, torch.rand(4, 1) + pi]
+    T = int(counts.sum())
+    res = {"counts": counts, **{k: torch.zeros(T) for k in ("e_pred_raw", "e_pred_avg_raw", "raw_nn_pred")}}
+    obj.fill_the_dicts2write(b, res, 1)
+    hd, ld = obj.high_dict_to_zip, obj.low_dict_to_zip
+    assert [a.shape for a in hd["e_part_0"]] == [(8,), (4,)] and [a.shape for a in ld["e_part_1"]] == [(2,), (1,)]
+    np.testing.assert_array_equal(hd["e_part_1"][0], b["high_e_part_1"][0][:, 0].numpy())
+    assert np.all(hd["e_part_1"][1] == 0) and hd["e_part_1"][1].shape == (4,)         # event 1 has one particle: index 1 is padding
+    assert np.all(hd["e_part_2"][0] == 0) and np.all(ld["e_part_2"][1] == 0)
+    with pytest.raises(KeyError, match="store_energy_incidence"):
+        obj.fill_the_dicts2write({k: v for k, v in b.items() if not k.startswith("low_e_part")}, res, 1)

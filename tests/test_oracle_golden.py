@@ -54,6 +54,26 @@ def test_oracle_matches_golden_config1_subset(golden_dir):
     torch.testing.assert_close(xs[g["n_steps"] // 2][m], refm[m], rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize("method", ["euler", "midpoint"])
+def test_oracle_matches_golden_multipart_subset(method, golden_dir):
+    """The six shortest of the 16 golden multipart events (16 ... 320 cells), re-run alone: their packed golden rows
+    (the golden is stored packed in entry order) must be reproduced by the oracle."""
+    g = torch.load(os.path.join(golden_dir, "sr_traj_multipart.pt"))
+    cfg, d, sd, dims = _setup("multipart", g["weight_seed"])
+    counts = np.array(g["counts"])
+    full = synthetic_events("multipart", len(counts), seed=g["event_seed"], counts=counts)
+    x0 = synthetic_noise(full, seed=g["noise_seed"])
+    a = len(counts) - 6
+    nmax = int(counts[a:].max())
+    sub = {k: (v[a:, :nmax].contiguous() if torch.is_tensor(v) else v) for k, v in full.items()}
+    with torch.no_grad():
+        xs = sr_oracle.generate_samples(sd, dims, sub, x0[a:, :nmax], n_steps=g["n_steps"], method=method, ret_seq=True)
+    m = sub["q_mask"]
+    off = int(counts[:a].sum())
+    torch.testing.assert_close(xs[-1][m][:, 0], g[method]["x_final"][off:], rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(xs[g["n_steps"] // 2][m][:, 0], g[method]["x_mid"][off:], rtol=1e-4, atol=1e-4)
+
+
 def test_oracle_dopri5_matches_golden(golden_dir):
     g = torch.load(os.path.join(golden_dir, "sr_dopri5_single_e.pt"))
     cfg, d, sd, dims = _setup("single_e", g["weight_seed"])
