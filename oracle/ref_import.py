@@ -1,7 +1,7 @@
-"""Import the UNMODIFIED reference modules from /root/reference (build container only).
+"""Import the UNMODIFIED reference modules: from /root/reference in the build container, from the byte-for-byte copy
+``oracle/_ref`` (made by oracle/make_ref.py, git-ignored, shipped with the snapshot) on the GPU box.
 
-TEST INFRASTRUCTURE.  /root/reference does not exist on the GPU box; callers must check
-``available()``.  ``models/flow_model.py`` imports ``torchdiffeq`` and ``torchcfm`` at module
+TEST INFRASTRUCTURE.  Callers must check ``available()``.  ``models/flow_model.py`` imports ``torchdiffeq`` and ``torchcfm`` at module
 top (lines 11-12); neither is installable here, so two stub modules are injected before the
 import.  The stubs are never executed on the paths we use:
 ``odeint`` is replaced by oracle/odeint.py and the flow matcher is training-only.
@@ -14,11 +14,24 @@ import os
 import sys
 import types
 
-REF_ROOT = "/root/reference"
+MOUNT = "/root/reference"
+COPY = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _has(root: str) -> bool:
+    return os.path.isfile(os.path.join(root, "models", "flow_model.py"))
+
+
+REF_ROOT = MOUNT if _has(MOUNT) or not _has(COPY) else COPY
 
 
 def available() -> bool:
-    return os.path.isfile(os.path.join(REF_ROOT, "models", "flow_model.py"))
+    return _has(REF_ROOT)
+
+
+def source() -> str:
+    """'mount' (/root/reference), 'copy' (oracle/_ref) or 'absent'."""
+    return "absent" if not available() else ("mount" if REF_ROOT == MOUNT else "copy")
 
 
 def _inject_stubs() -> None:
@@ -36,7 +49,7 @@ def _inject_stubs() -> None:
 def import_reference():
     """Returns (FlowModel, SAPF) classes of the reference."""
     if not available():
-        raise RuntimeError("/root/reference is not present on this machine")
+        raise RuntimeError("neither /root/reference nor oracle/_ref is present on this machine")
     _inject_stubs()
     if REF_ROOT not in sys.path:
         sys.path.append(REF_ROOT)          # appended, never first (its lightning.py shadows PyPI's)
