@@ -164,6 +164,10 @@ int bf16_pack_weights(SrhepHandle* h, const float* wh) {
     CK(h, cudaFuncSetAttribute(attn2_bf16_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CK(h, cudaFuncSetAttribute(attn2_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAtt2SmemBytes));
     CK(h, cudaFuncSetAttribute(attn2_bf16_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(h, cudaFuncSetAttribute(attn3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Att3Cfg<false>::kSmemBytes));
+    CK(h, cudaFuncSetAttribute(attn3_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(h, cudaFuncSetAttribute(attn3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Att3Cfg<false>::kSmemBytes));
+    CK(h, cudaFuncSetAttribute(attn3_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CK(h, cudaFuncSetAttribute(head_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeadSmemBytes));
     CK(h, cudaFuncSetAttribute(layer_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemBytes));
     CK(h, cudaFuncSetAttribute(layer_chain_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -227,7 +231,7 @@ void launch_attn_bf16(Engine& E, const Pass& p, __nv_bfloat16* out) {
     AttnBf16Params q;
     static_assert(sizeof(AttnItem) == sizeof(AttnWork), "work item layout");
     q.items = reinterpret_cast<const AttnItem*>(h->attn_work + p.w0); q.n_items = p.w1 - p.w0;
-    q.out = out; q.ldo = d.h_dim; q.h_dim = d.h_dim;
+    q.out = out; q.out_lo = nullptr; q.ldo = d.h_dim; q.h_dim = d.h_dim;
     q.scale_log2 = 1.4426950408889634f / sqrtf((float)(d.h_dim / d.heads));
     q.fp16 = h->precision == SRHEP_PREC_FP16;
     q.dbg = nullptr;
@@ -235,8 +239,11 @@ void launch_attn_bf16(Engine& E, const Pass& p, __nv_bfloat16* out) {
     static int adbg_calls = 0;
     const bool dbg = h->sw.attn_dbg && (++adbg_calls == 8);
     if (dbg) { if (!adbg) cudaMalloc(&adbg, 256 * sizeof(long long)); cudaMemsetAsync(adbg, 0, 256 * sizeof(long long), E.s); q.dbg = adbg; }
-    dim3 grid(std::max(1, std::min(q.n_items, 2 * 148 / d.heads)), d.heads);
-    if (!h->sw.attn_v1) {
+    dim3 grid(std::max(1, std::min(q.n_items, h->sw.ctas_per_sm * 148 / d.heads)), d.heads);
+    if (!h->sw.attn_v1 && !h->sw.attn_v2) {        // third generation: P in tensor memory, producer running ahead across items
+        if (q.fp16) attn3_kernel<true, false><<<grid, kAtt3Threads, Att3Cfg<false>::kSmemBytes, E.s>>>(h->bw.tm_qkv, h->bw.tm_kv64, h->bw.tm_qkv, h->bw.tm_kv64, q);
+        else attn3_kernel<false, false><<<grid, kAtt3Threads, Att3Cfg<false>::kSmemBytes, E.s>>>(h->bw.tm_qkv, h->bw.tm_kv64, h->bw.tm_qkv, h->bw.tm_kv64, q);
+    } else if (!h->sw.attn_v1) {
         if (q.fp16) attn2_bf16_kernel<true><<<grid, kAtt2Threads, kAtt2SmemBytes, E.s>>>(h->bw.tm_qkv, h->bw.tm_kv64, q);
         else attn2_bf16_kernel<false><<<grid, kAtt2Threads, kAtt2SmemBytes, E.s>>>(h->bw.tm_qkv, h->bw.tm_kv64, q);
     }
@@ -282,7 +289,7 @@ void launch_chain(Engine& E, int M, int l, const int* rev) {
         q.qkv = h->qkv_lp;
     }
     const int m_tiles = (M + 127) / 128;
-    const int grid = std::max(1, std::min(m_tiles, 2 * 148));
+    const int grid = std::max(1, std::min(m_tiles, h->sw.ctas_per_sm * 148));
     static long long* dbg_dev = nullptr;
     const bool dbg = h->sw.chain_dbg && l == 1;
     if (dbg) { if (!dbg_dev) cudaMalloc(&dbg_dev, 256 * sizeof(long long)); cudaMemsetAsync(dbg_dev, 0, 256 * sizeof(long long), E.s); q.dbg = dbg_dev; }
@@ -325,7 +332,7 @@ void launch_chain_first(Engine& E, int M, const int* rev) {
     q.ld_mod = h->mod_width;
     q.qkv = h->qkv_lp;
     const int m_tiles = (M + 127) / 128;
-    const int grid = std::max(1, std::min(m_tiles, 2 * 148));
+    const int grid = std::max(1, std::min(m_tiles, h->sw.ctas_per_sm * 148));
     if (q.fp16) layer_chain_kernel<true, true><<<grid, kChainThreads, kChainSmemBytes, E.s>>>(bw.tm_tok, q);
     else layer_chain_kernel<false, true><<<grid, kChainThreads, kChainSmemBytes, E.s>>>(bw.tm_tok, q);
     E.check("layer_chain_first");

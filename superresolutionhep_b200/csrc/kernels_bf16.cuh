@@ -707,6 +707,7 @@ struct AttnItem { int q_row, q_len, k_row, k_len; };     // same layout as AttnW
 struct AttnBf16Params {
     const AttnItem* items; int n_items;
     __nv_bfloat16* out; int ldo;      // [rows, h_dim]
+    __nv_bfloat16* out_lo;            // split (fp32-grade) mode: low plane of the output (kernels_attn3.cuh)
     int h_dim;                        // column offsets: q = head*64, k = h_dim + head*64, v = 2*h_dim + head*64
     float scale_log2;                 // log2(e) / sqrt(head_dim)
     int fp16;                         // 0 = bf16, 1 = fp16 operands / output

@@ -21,6 +21,7 @@
 #include "kernels_chain.cuh"
 #include "kernels_head.cuh"
 #include "kernels_attn.cuh"
+#include "kernels_attn3.cuh"
 #include "kernels_embed.cuh"
 #include "kernels_ode.cuh"
 
@@ -112,7 +113,7 @@ struct SrhepHandle {
     int mod_width = 0;
 
     // diagnostic switches (environment, read once per API call: A/B comparisons in the tests and tools)
-    struct Switches { bool no_chain = false, no_chain_first = false, attn_simt = false, attn_v1 = false, no_lnfuse = false, head_fp32 = false, no_headchain = false, no_embed_tc = false, head_prep_scalar = false, chain_dbg = false, attn_dbg = false; } sw;
+    struct Switches { bool no_chain = false, no_chain_first = false, attn_simt = false, attn_v1 = false, attn_v2 = false, no_lnfuse = false, head_fp32 = false, no_headchain = false, no_embed_tc = false, head_prep_scalar = false, chain_dbg = false, attn_dbg = false; int ctas_per_sm = 2; } sw;
     // options
     int64_t pass_tokens = 0;
     int use_graph = 1;
@@ -199,9 +200,10 @@ int dev_alloc(SrhepHandle* h, T*& p, size_t n) {
 bool is_lp(const SrhepHandle* h) { return h->precision != SRHEP_PREC_FP32; }
 void read_switches(SrhepHandle* h) {
     auto on = [](const char* n) { const char* v = getenv(n); return v && *v && *v != '0'; };
-    h->sw.no_chain = on("SRHEP_NO_CHAIN"); h->sw.no_chain_first = on("SRHEP_NO_CHAIN_FIRST"); h->sw.attn_simt = on("SRHEP_ATTN_SIMT"); h->sw.attn_v1 = on("SRHEP_ATTN_V1");
+    h->sw.no_chain = on("SRHEP_NO_CHAIN"); h->sw.no_chain_first = on("SRHEP_NO_CHAIN_FIRST"); h->sw.attn_simt = on("SRHEP_ATTN_SIMT"); h->sw.attn_v1 = on("SRHEP_ATTN_V1"); h->sw.attn_v2 = on("SRHEP_ATTN_V2");
     h->sw.no_lnfuse = on("SRHEP_NO_LNFUSE"); h->sw.head_fp32 = on("SRHEP_HEAD_FP32"); h->sw.no_headchain = on("SRHEP_NO_HEADCHAIN"); h->sw.no_embed_tc = on("SRHEP_NO_EMBED_TC"); h->sw.head_prep_scalar = on("SRHEP_HEAD_PREP_SCALAR");
     h->sw.chain_dbg = on("SRHEP_CHAIN_DBG"); h->sw.attn_dbg = on("SRHEP_ATTN_DBG");
+    { const char* v = getenv("SRHEP_CTAS_PER_SM"); h->sw.ctas_per_sm = (v && *v == '1') ? 1 : 2; }      // persistent grids of the chain / attention kernels: CTAs per SM
 }
 size_t act_elem_size(const SrhepHandle* h) { return is_lp(h) ? 2 : 4; }
 
@@ -850,7 +852,7 @@ int srhep_bind_events(SrhepHandle* h, const SrhepCond* c, const int32_t* cu, int
     // event stay neighbours and still share their K/V tiles in L2.  Results do not depend on the order (items are independent).
     for (const Pass& p : h->passes) {
         const int n = p.w1 - p.w0;
-        const int G = std::max(1, std::min(n, 2 * 148 / h->d.heads));
+        const int G = std::max(1, std::min(n, h->sw.ctas_per_sm * 148 / h->d.heads));
         auto first = work.begin() + p.w0, last = work.begin() + p.w1;
         std::stable_sort(first, last, [](const AttnWork& a, const AttnWork& b) { return a.k_len > b.k_len; });
         for (int r0 = G; r0 < n; r0 += 2 * G) std::reverse(first + r0, first + std::min(n, r0 + G));
