@@ -41,7 +41,8 @@ uint16_t f2bf(float f) {
 }
 
 // W fp32 [N, K] (row pitch ldw) -> image [N / BN][kpad / 64][BN rows x 128 B], 128B-swizzled, K zero-padded
-void pack_weight(std::vector<uint8_t>& img, size_t off, const float* W, int ldw, int N, int K, int kpad, int BN, bool fp16) {
+// plane = 1: the LOW fp16 plane of the split mode, fp16(w - float(fp16(w)))
+void pack_weight(std::vector<uint8_t>& img, size_t off, const float* W, int ldw, int N, int K, int kpad, int BN, bool fp16, int plane = 0, float mul = 1.f) {
     const int nkb = kpad / 64;
     for (int n = 0; n < N; ++n) {
         const int nt = n / BN, nr = n % BN;
@@ -51,7 +52,9 @@ void pack_weight(std::vector<uint8_t>& img, size_t off, const float* W, int ldw,
                 uint16_t* dst = reinterpret_cast<uint16_t*>(row + ((c ^ (nr & 7)) * 16));
                 for (int j = 0; j < 8; ++j) {
                     const int k = kb * 64 + c * 8 + j;
-                    dst[j] = k < K ? (fp16 ? f2h(W[(size_t)n * ldw + k]) : f2bf(W[(size_t)n * ldw + k])) : (uint16_t)0;
+                    const float wv = k < K ? W[(size_t)n * ldw + k] * mul : 0.f;      // mul is a power of two: exact
+                    if (plane) { const __half hv = __float2half_rn(wv); dst[j] = f2h(wv - __half2float(hv)); }
+                    else dst[j] = k < K ? (fp16 ? f2h(wv) : f2bf(wv)) : (uint16_t)0;
                 }
             }
         }
@@ -73,21 +76,38 @@ int bf16_pack_weights(SrhepHandle* h, const float* wh) {
     for (int l = 0; l < d.layers; ++l) { bw.qkv[l] = take(3 * H, H); bw.out[l] = take(H, H); bw.mlp1[l] = take(H, H); bw.mlp2[l] = take(H, H); }
     const int hk = d.v_in + d.ctx;
     bw.head1 = take(d.head_h1, hk);
-    bw.head_chain = hk == kHeadK1 && d.head_h1 == kHeadH1 && d.head_h2 == kHeadH2 && d.head_h3 == kHeadH3;
+    bw.head_chain = hk == kHeadK1 && d.head_h1 == kHeadH1 && d.head_h2 == kHeadH2 && d.head_h3 == kHeadH3 && !h->split;      // split mode: the head runs in fp32 on the CUDA cores
     if (bw.head_chain) { bw.head2 = take(kHeadH2, kHeadH1); bw.head3 = take(kHeadH3, kHeadH2); }
     bw.embed_tc = d.etaphi_in == 3 && d.etaphi_hid == 64 && d.proxy_hid == 64 && d.noisy_hid == 64 && d.etaphi_out == 32 && d.proxy_out == 31 &&
-                  d.noisy_out == 64 && d.layer_out == 32 && d.t_emb == 64 && d.cond == 96;
+                  d.noisy_out == 64 && d.layer_out == 32 && d.t_emb == 64 && d.cond == 96 && !h->split;
     if (bw.embed_tc) bw.embed_w = take(128, 64);
     std::vector<uint8_t> img(off);
     const bool fp16 = h->precision == SRHEP_PREC_FP16;
-    pack_weight(img, bw.feat0, wh + L.feat0.w, L.feat0.in, H, ncol, bw.feat0_kpad, 256, fp16);
+    // split mode: each matrix is stored as W * 2^s with max |W| 2^s in [256, 512), so that the LOW plane (~2^-12 of the value) is a normal fp16
+    // number for every weight that matters (as stored, the weights are ~0.06 and their low planes would be subnormals with an absolute
+    // quantum of 6e-8: 5e-7 of the weight); 2^-s goes to the kernel, which applies it to the accumulator (exact)
+    auto pow2_scale = [&](const float* W, int ldw, int N, int K) -> float {
+        if (!h->split) return 1.f;
+        float mx = 0.f;
+        for (int n = 0; n < N; ++n) for (int k = 0; k < K; ++k) mx = std::max(mx, fabsf(W[(size_t)n * ldw + k]));
+        if (!(mx > 0.f) || !std::isfinite(mx)) return 1.f;
+        int e; frexpf(mx, &e);                       // mx = f * 2^e, f in [0.5, 1)
+        return ldexpf(1.f, 9 - e);                   // mx * 2^(9-e) in [256, 512)
+    };
+    float m_feat0 = pow2_scale(wh + L.feat0.w, L.feat0.in, H, ncol);
+    bw.ws_feat0 = 1.f / m_feat0;
+    std::vector<float> m_qkv(3 * d.layers, 1.f), m_out(d.layers, 1.f), m_m1(d.layers, 1.f), m_m2(d.layers, 1.f);
+    pack_weight(img, bw.feat0, wh + L.feat0.w, L.feat0.in, H, ncol, bw.feat0_kpad, 256, fp16, 0, m_feat0);
     for (int l = 0; l < d.layers; ++l) {
         const Layout::Layer& y = L.layers[l];
         const Lin* qkv[3] = {&y.q, &y.k, &y.v};
-        for (int j = 0; j < 3; ++j) pack_weight(img, bw.qkv[l] + (size_t)j * H * H * 2, wh + qkv[j]->w, H, H, H, H, 256, fp16);
-        pack_weight(img, bw.out[l], wh + y.o.w, H, H, H, H, 256, fp16);
-        pack_weight(img, bw.mlp1[l], wh + y.m1.w, H, H, H, H, 256, fp16);
-        pack_weight(img, bw.mlp2[l], wh + y.m2.w, H, H, H, H, 256, fp16);
+        for (int j = 0; j < 3; ++j) { m_qkv[3 * l + j] = pow2_scale(wh + qkv[j]->w, H, H, H); bw.ws_qkv[l][j] = 1.f / m_qkv[3 * l + j]; }
+        m_out[l] = pow2_scale(wh + y.o.w, H, H, H); m_m1[l] = pow2_scale(wh + y.m1.w, H, H, H); m_m2[l] = pow2_scale(wh + y.m2.w, H, H, H);
+        bw.ws_out[l] = 1.f / m_out[l]; bw.ws_mlp1[l] = 1.f / m_m1[l]; bw.ws_mlp2[l] = 1.f / m_m2[l];
+        for (int j = 0; j < 3; ++j) pack_weight(img, bw.qkv[l] + (size_t)j * H * H * 2, wh + qkv[j]->w, H, H, H, H, 256, fp16, 0, m_qkv[3 * l + j]);
+        pack_weight(img, bw.out[l], wh + y.o.w, H, H, H, H, 256, fp16, 0, m_out[l]);
+        pack_weight(img, bw.mlp1[l], wh + y.m1.w, H, H, H, H, 256, fp16, 0, m_m1[l]);
+        pack_weight(img, bw.mlp2[l], wh + y.m2.w, H, H, H, H, 256, fp16, 0, m_m2[l]);
     }
     // The velocity head ends in a 32-term dot product with cancellation: its operand rounding dominates the error of v (bf16 operands: rel-L2 2e-2
     // on v for 3e-3 on the transformer output).  Every head operand is a LayerNorm output or a weight, far inside fp16 range, so the fused
@@ -129,6 +149,20 @@ int bf16_pack_weights(SrhepHandle* h, const float* wh) {
     }
     CK(h, cudaMalloc(&bw.img, img.size()));
     CK(h, cudaMemcpy(bw.img, img.data(), img.size(), cudaMemcpyHostToDevice));
+    if (h->split) {      // low planes of the chain's weights at the same offsets
+        std::vector<uint8_t> lo(off, 0);
+        pack_weight(lo, bw.feat0, wh + L.feat0.w, L.feat0.in, H, ncol, bw.feat0_kpad, 256, true, 1, m_feat0);
+        for (int l = 0; l < d.layers; ++l) {
+            const Layout::Layer& y = L.layers[l];
+            const Lin* qkv[3] = {&y.q, &y.k, &y.v};
+            for (int j = 0; j < 3; ++j) pack_weight(lo, bw.qkv[l] + (size_t)j * H * H * 2, wh + qkv[j]->w, H, H, H, H, 256, true, 1, m_qkv[3 * l + j]);
+            pack_weight(lo, bw.out[l], wh + y.o.w, H, H, H, H, 256, true, 1, m_out[l]);
+            pack_weight(lo, bw.mlp1[l], wh + y.m1.w, H, H, H, H, 256, true, 1, m_m1[l]);
+            pack_weight(lo, bw.mlp2[l], wh + y.m2.w, H, H, H, H, 256, true, 1, m_m2[l]);
+        }
+        CK(h, cudaMalloc(&bw.img_lo, lo.size()));
+        CK(h, cudaMemcpy(bw.img_lo, lo.data(), lo.size(), cudaMemcpyHostToDevice));
+    }
     bw.bytes = img.size();
     bw.bias_layer_stride = 7 * (size_t)H;      // out.b | mlp1.b | mlp2.b | norm1.w | norm1.b | norm2.w | norm2.b
     bw.bias_head1 = bw.bias_layer_stride * d.layers;
@@ -178,11 +212,18 @@ int bf16_pack_weights(SrhepHandle* h, const float* wh) {
     CK(h, cudaFuncSetAttribute(layer_chain_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemBytes));
     CK(h, cudaFuncSetAttribute(layer_chain_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CK(h, cudaFuncSetAttribute(gemm_bf16_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_bf16_smem_bytes<128>(hk / 64)));
+    if (h->split) {
+        CK(h, cudaFuncSetAttribute(layer_chain_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemBytesSplit));
+        CK(h, cudaFuncSetAttribute(layer_chain_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemBytesSplit));
+        CK(h, cudaFuncSetAttribute(attn3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Att3Cfg<true>::kSmemBytes));
+    }
     return 0;
 }
 
 void bf16_free_weights(SrhepHandle* h) {
     if (h->bw.img) cudaFree(h->bw.img);
+    if (h->bw.img_lo) cudaFree(h->bw.img_lo);
+    if (h->bw.tok_lp_lo) cudaFree(h->bw.tok_lp_lo);
     if (h->bw.bias) cudaFree(h->bw.bias);
     if (h->bw.tok_lp) cudaFree(h->bw.tok_lp);
     free(h->bw.bias_h); free(h->bw.bqkv_h);
@@ -204,6 +245,15 @@ int bf16_on_bind(SrhepHandle* h) {
     if ((rc = make_a_tmap(h, &bw.tm_tok, bw.tok_lp, R, bw.feat0_kpad, bw.feat0_kpad))) return rc;
     if ((rc = make_a_tmap(h, &bw.tm_qkv, h->qkv_lp, R, 3 * d.h_dim, 3 * d.h_dim))) return rc;
     if ((rc = make_a_tmap(h, &bw.tm_kv64, h->qkv_lp, R, 3 * d.h_dim, 3 * d.h_dim, kAtt2KvTile))) return rc;
+    if (h->split) {
+        if (bw.tok_lp_lo) { CK(h, cudaFree(bw.tok_lp_lo)); bw.tok_lp_lo = nullptr; }
+        CK(h, cudaMalloc(&bw.tok_lp_lo, R * bw.feat0_kpad * 2));
+        CK(h, cudaMemset(bw.tok_lp_lo, 0, R * bw.feat0_kpad * 2));
+        if ((rc = make_a_tmap(h, &bw.tm_b_lo, h->act_b_lo, R, d.h_dim, d.h_dim))) return rc;
+        if ((rc = make_a_tmap(h, &bw.tm_tok_lo, bw.tok_lp_lo, R, bw.feat0_kpad, bw.feat0_kpad))) return rc;
+        if ((rc = make_a_tmap(h, &bw.tm_qkv_lo, h->qkv_lo, R, 3 * d.h_dim, 3 * d.h_dim))) return rc;
+        if ((rc = make_a_tmap(h, &bw.tm_kv64_lo, h->qkv_lo, R, 3 * d.h_dim, 3 * d.h_dim, kAtt2KvTile))) return rc;
+    }
     return 0;
 }
 
@@ -231,7 +281,7 @@ void launch_attn_bf16(Engine& E, const Pass& p, __nv_bfloat16* out) {
     AttnBf16Params q;
     static_assert(sizeof(AttnItem) == sizeof(AttnWork), "work item layout");
     q.items = reinterpret_cast<const AttnItem*>(h->attn_work + p.w0); q.n_items = p.w1 - p.w0;
-    q.out = out; q.out_lo = nullptr; q.ldo = d.h_dim; q.h_dim = d.h_dim;
+    q.out = out; q.out_lo = h->split ? (__nv_bfloat16*)h->act_b_lo : nullptr; q.ldo = d.h_dim; q.h_dim = d.h_dim;
     q.scale_log2 = 1.4426950408889634f / sqrtf((float)(d.h_dim / d.heads));
     q.fp16 = h->precision == SRHEP_PREC_FP16;
     q.dbg = nullptr;
@@ -240,6 +290,10 @@ void launch_attn_bf16(Engine& E, const Pass& p, __nv_bfloat16* out) {
     const bool dbg = h->sw.attn_dbg && (++adbg_calls == 8);
     if (dbg) { if (!adbg) cudaMalloc(&adbg, 256 * sizeof(long long)); cudaMemsetAsync(adbg, 0, 256 * sizeof(long long), E.s); q.dbg = adbg; }
     dim3 grid(std::max(1, std::min(q.n_items, h->sw.ctas_per_sm * 148 / d.heads)), d.heads);
+    if (h->split) {                                 // fp32-grade: (hi, lo) planes, one CTA per SM
+        dim3 g1(std::max(1, std::min(q.n_items, 148 / d.heads)), d.heads);
+        attn3_kernel<true, true><<<g1, kAtt3Threads, Att3Cfg<true>::kSmemBytes, E.s>>>(h->bw.tm_qkv, h->bw.tm_kv64, h->bw.tm_qkv_lo, h->bw.tm_kv64_lo, q);
+    } else
     if (!h->sw.attn_v1 && !h->sw.attn_v2) {        // third generation: P in tensor memory, producer running ahead across items
         if (q.fp16) attn3_kernel<true, false><<<grid, kAtt3Threads, Att3Cfg<false>::kSmemBytes, E.s>>>(h->bw.tm_qkv, h->bw.tm_kv64, h->bw.tm_qkv, h->bw.tm_kv64, q);
         else attn3_kernel<false, false><<<grid, kAtt3Threads, Att3Cfg<false>::kSmemBytes, E.s>>>(h->bw.tm_qkv, h->bw.tm_kv64, h->bw.tm_qkv, h->bw.tm_kv64, q);
@@ -283,18 +337,23 @@ void launch_chain(Engine& E, int M, int l, const int* rev) {
     if (!last) {
         const float* mn = h->mod + (size_t)(l + 1) * 6 * H;
         for (int j = 0; j < 3; ++j) q.w[3 + j] = bw.img + bw.qkv[l + 1] + (size_t)j * H * H * 2;
+        q.qkv_lo = h->qkv_lo;
         memcpy(q.cst[3], bw.bqkv_h + (size_t)(l + 1) * 3 * H, 3 * H * sizeof(float));
         memcpy(q.cst[8], bw.bias_h + (l + 1) * bw.bias_layer_stride + 3 * H, 2 * H * sizeof(float));     // next norm1 w | b
         q.shift_nxt = mn; q.scale_nxt = mn + H;
         q.qkv = h->qkv_lp;
     }
     const int m_tiles = (M + 127) / 128;
-    const int grid = std::max(1, std::min(m_tiles, h->sw.ctas_per_sm * 148));
+    const int grid = std::max(1, std::min(m_tiles, (h->split ? 1 : h->sw.ctas_per_sm) * 148));
+    if (h->split) for (int g = 0; g < 6; ++g) q.w_lo[g] = q.w[g] ? bw.img_lo + (q.w[g] - bw.img) : nullptr;
+    q.wscale[0] = bw.ws_out[l]; q.wscale[1] = bw.ws_mlp1[l]; q.wscale[2] = bw.ws_mlp2[l];
+    for (int j = 0; j < 3; ++j) q.wscale[3 + j] = last ? 1.f : bw.ws_qkv[l + 1][j];
     static long long* dbg_dev = nullptr;
     const bool dbg = h->sw.chain_dbg && l == 1;
     if (dbg) { if (!dbg_dev) cudaMalloc(&dbg_dev, 256 * sizeof(long long)); cudaMemsetAsync(dbg_dev, 0, 256 * sizeof(long long), E.s); q.dbg = dbg_dev; }
-    if (q.fp16) layer_chain_kernel<true><<<grid, kChainThreads, kChainSmemBytes, E.s>>>(bw.tm_b, q);
-    else layer_chain_kernel<false><<<grid, kChainThreads, kChainSmemBytes, E.s>>>(bw.tm_b, q);
+    if (h->split) layer_chain_kernel<true, false, true><<<grid, kChainThreads, kChainSmemBytesSplit, E.s>>>(bw.tm_b, bw.tm_b_lo, q);
+    else if (q.fp16) layer_chain_kernel<true><<<grid, kChainThreads, kChainSmemBytes, E.s>>>(bw.tm_b, bw.tm_b, q);
+    else layer_chain_kernel<false><<<grid, kChainThreads, kChainSmemBytes, E.s>>>(bw.tm_b, bw.tm_b, q);
     E.check("layer_chain");
     if (dbg) {
         long long hbuf[256];
@@ -330,11 +389,14 @@ void launch_chain_first(Engine& E, int M, const int* rev) {
     q.shift_nxt = h->mod; q.scale_nxt = h->mod + H;                    // layer 0 shift_msa | scale_msa
     q.gate_msa = q.shift_mlp = q.scale_mlp = q.gate_mlp = h->mod;      // unused in this mode
     q.ld_mod = h->mod_width;
-    q.qkv = h->qkv_lp;
+    q.qkv = h->qkv_lp; q.qkv_lo = h->qkv_lo;
     const int m_tiles = (M + 127) / 128;
-    const int grid = std::max(1, std::min(m_tiles, h->sw.ctas_per_sm * 148));
-    if (q.fp16) layer_chain_kernel<true, true><<<grid, kChainThreads, kChainSmemBytes, E.s>>>(bw.tm_tok, q);
-    else layer_chain_kernel<false, true><<<grid, kChainThreads, kChainSmemBytes, E.s>>>(bw.tm_tok, q);
+    const int grid = std::max(1, std::min(m_tiles, (h->split ? 1 : h->sw.ctas_per_sm) * 148));
+    if (h->split) for (int g = 0; g < 6; ++g) q.w_lo[g] = q.w[g] ? bw.img_lo + (q.w[g] - bw.img) : nullptr;
+    q.wscale[0] = bw.ws_feat0; for (int j = 0; j < 3; ++j) q.wscale[1 + j] = bw.ws_qkv[0][j];
+    if (h->split) layer_chain_kernel<true, true, true><<<grid, kChainThreads, kChainSmemBytesSplit, E.s>>>(bw.tm_tok, bw.tm_tok_lo, q);
+    else if (q.fp16) layer_chain_kernel<true, true><<<grid, kChainThreads, kChainSmemBytes, E.s>>>(bw.tm_tok, bw.tm_tok, q);
+    else layer_chain_kernel<false, true><<<grid, kChainThreads, kChainSmemBytes, E.s>>>(bw.tm_tok, bw.tm_tok, q);
     E.check("layer_chain_first");
 }
 
@@ -345,7 +407,7 @@ void bf16_forward(Engine& E, const Pass& p, const int* rev, const StageRef& st) 
     const int fp16 = h->precision == SRHEP_PREC_FP16;
     float* x = h->xres;
     const float* mod = h->mod;
-    const bool chain = (H == kChainH && d.mlp_hid == kChainH) && !h->sw.no_chain;
+    const bool chain = (H == kChainH && d.mlp_hid == kChainH) && (!h->sw.no_chain || h->split);      // split mode exists for the chain path only
     E.x_blocked = chain;
     __nv_bfloat16* a = (__nv_bfloat16*)h->act_a; __nv_bfloat16* b = (__nv_bfloat16*)h->act_b;
     __nv_bfloat16* qkv = (__nv_bfloat16*)h->qkv_lp;
@@ -359,7 +421,7 @@ void bf16_forward(Engine& E, const Pass& p, const int* rev, const StageRef& st) 
         if (!second) { ep.ln_w = bl + 3 * H; ep.ln_b = bl + 4 * H; ep.ln_shift = ml; ep.ln_scale = ml + H; }
         else { ep.ln_w = bl + 5 * H; ep.ln_b = bl + 6 * H; ep.ln_shift = ml + 3 * H; ep.ln_scale = ml + 4 * H; }
     };
-    const bool first_fused = chain && bw.feat0_kpad == 192 && !h->sw.no_chain_first;
+    const bool first_fused = chain && bw.feat0_kpad == 192 && (!h->sw.no_chain_first || h->split);
     if (first_fused) launch_chain_first(E, M, rev);
     else
     { GemmEpilogue ep; ep.row_bias = h->f0bias; ep.ld_row_bias = H; ep.row_event = rev; ep.act = 1;
@@ -411,7 +473,7 @@ void bf16_forward(Engine& E, const Pass& p, const int* rev, const StageRef& st) 
     }
     E.cat = SRHEP_CAT_HEAD;
     const int hw = d.v_in + d.ctx;
-    if (h->sw.head_fp32) {
+    if (h->sw.head_fp32 || h->split) {
         E.head_prep<float>(E.head_params(p, x), (float*)h->act_a, hw);
         GemmEpilogue ep; ep.bias = E.W(L.h1.b); ep.act = 1;
         E.gemm_f32<float>((float*)h->act_a, hw, E.W(L.h1.w), hw, h->h1buf, d.head_h1, M, d.head_h1, hw, ep);

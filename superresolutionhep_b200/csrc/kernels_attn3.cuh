@@ -54,14 +54,6 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
         : "memory");
 }
 
-// x -> (hi, lo) fp16 planes with x = hi + lo up to 2^-22 |x| (lo may be subnormal: tensor cores take fp16 subnormals at full rate)
-__device__ __forceinline__ void split16(float a, float b, uint32_t& hi, uint32_t& lo) {
-    const __half2 h = __floats2half2_rn(a, b);
-    const float2 hf = __half22float2(h);
-    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
-    hi = *reinterpret_cast<const uint32_t*>(&h); lo = *reinterpret_cast<const uint32_t*>(&l);
-}
-
 // One key tile of one query row: scores (64, or 32 when the second half of a ragged tile is all padding) -> P = exp2(S c - m)
 // as the 16-bit A operand in tensor memory, running sum and lazy running maximum.
 template <bool kFp16, bool kSplit, bool kHalf2>

@@ -190,6 +190,14 @@ __device__ __forceinline__ uint32_t pack16(float lo, float hi, int fp16) {
     return pack_bf16x2(lo, hi);
 }
 
+// x -> (hi, lo) fp16 planes with x = hi + lo up to 2^-22 |x| (lo may be subnormal: tensor cores take fp16 subnormals at full rate)
+__device__ __forceinline__ void split16(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h); lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
 // ------------------------------------------------------------------------------------
 // GEMM  C[M, N] = epilogue(A[M, K] . W[N, K]^T)      A, W bf16; fp32 accumulation in TMEM
 //
@@ -945,6 +953,11 @@ struct Bf16Weights {
     CUtensorMap tm_ln, tm_hin, tm_b, tm_tok;      // A-operand maps over the pass workspace
     CUtensorMap tm_qkv;                           // q|k|v tiles for the attention kernel (128-row boxes)
     CUtensorMap tm_kv64;                          // same matrix, 64-row boxes (key/value tiles of the second-generation attention)
+    // split (fp32-grade) mode: the low planes of the weights (same offsets as in img) and of the activation operands
+    uint8_t* img_lo = nullptr;
+    float ws_feat0 = 1.f, ws_qkv[64][3], ws_out[64], ws_mlp1[64], ws_mlp2[64];     // 2^-s of each chain weight matrix (its images hold W * 2^s)
+    __nv_bfloat16* tok_lp_lo = nullptr;
+    CUtensorMap tm_b_lo, tm_tok_lo, tm_qkv_lo, tm_kv64_lo;
 };
 
 }  // namespace srhep

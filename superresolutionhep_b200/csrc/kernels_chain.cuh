@@ -30,6 +30,9 @@ constexpr int kChainSlots = 3;
 constexpr uint32_t kChainSlotBytes = 16384;          // 128 weight rows x 128 B
 constexpr uint32_t kChainABytes = 65536;             // 4 k-blocks x (128 rows x 128 B)
 constexpr size_t kChainSmemBytes = kChainABytes + kChainSlots * kChainSlotBytes + 128;
+// split (fp32-grade) mode: every 16-bit operand is a pair of fp16 planes (hi, lo), each product runs as hi.hi + hi.lo + lo.hi
+// on the same fp32 accumulator (kernels_attn3.cuh: split16); the A buffer and the weight slots double, one CTA per SM
+constexpr size_t kChainSmemBytesSplit = 2 * kChainABytes + kChainSlots * 2 * kChainSlotBytes + 128;
 constexpr int kChainH = 256;
 constexpr int kChainStageEv = 16;                    // events per tile whose adaLN rows are staged in shared memory (3 KB each, after the 4 KB statistics scratch)
 
@@ -40,6 +43,8 @@ struct ChainParams {
     const int* row_event;        // [M] global event id of each row
     float* x;                    // fp32 residual stream in the BLOCKED layout (common.cuh: xblk_index), updated in place
     const uint8_t* w[6];         // pre-swizzled weight images [4 k-blocks][256 rows x 128 B]
+    const uint8_t* w_lo[6];      // split mode: the low planes of the same weights
+    float wscale[6];             // split mode: the images hold W * 2^s (s per matrix, so that the low plane stays out of the fp16 subnormals); this is 2^-s, applied to the accumulator
     float cst[10][256];          // per-column constants BY VALUE (constant bank, no LSU traffic): biases of stages 0-5, norm2 w/b, next norm1 w/b
     const float* gate_msa;       // per-event rows (stride ld_mod floats)
     const float* shift_mlp; const float* scale_mlp; const float* gate_mlp;
@@ -47,6 +52,7 @@ struct ChainParams {
     int ld_mod;
     const float* row_bias; int ld_row_bias;   // first-layer mode only: per-event bias rows of feat_0 (its context part)
     void* qkv;                   // [M, 768] 16-bit q|k|v of the next layer
+    void* qkv_lo;                // split mode: its low plane
     long long* dbg;              // optional timeline of CTA 0 (clock64 stamps, 32 per tile, first 8 tiles); null in production
 };
 
@@ -64,9 +70,9 @@ __device__ __forceinline__ float sum_f32x2(uint64_t v) { return f32x2_lo(v) + f3
 // acc + bias (+ LeakyReLU), gated into the residual: returns the new residual chunk in r[] (as bits).  Everything whose operands
 // already sit in registers runs as packed f32x2 instructions (two columns per FFMA2 / FADD2): at the power cap the epilogue's
 // instruction count is what the chain pays for.  s1 / s2 are PAIRS of partial sums (even / odd columns).
-template <bool kAct>
+template <bool kAct, bool kScaled = false>
 __device__ __forceinline__ void chain_resid_chunk(uint32_t (&r)[32], const float (&xr)[32], const float* bias /*constant bank*/,
-                                                  bool staged, uint32_t gate_sm, const float* __restrict__ gate, uint64_t& s1, uint64_t& s2) {
+                                                  bool staged, uint32_t gate_sm, const float* __restrict__ gate, uint64_t& s1, uint64_t& s2, float ws = 1.f) {
     const uint64_t slope2 = pack_f32x2(kLeaky, kLeaky);
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
@@ -74,7 +80,9 @@ __device__ __forceinline__ void chain_resid_chunk(uint32_t (&r)[32], const float
         const uint64_t gg[2] = {pack_f32x2(g4.x, g4.y), pack_f32x2(g4.z, g4.w)};
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-            float w0 = __uint_as_float(r[j + 2 * u]) + bias[j + 2 * u], w1 = __uint_as_float(r[j + 2 * u + 1]) + bias[j + 2 * u + 1];
+            float w0, w1;
+            if (kScaled) { w0 = fmaf(__uint_as_float(r[j + 2 * u]), ws, bias[j + 2 * u]); w1 = fmaf(__uint_as_float(r[j + 2 * u + 1]), ws, bias[j + 2 * u + 1]); }
+            else { w0 = __uint_as_float(r[j + 2 * u]) + bias[j + 2 * u]; w1 = __uint_as_float(r[j + 2 * u + 1]) + bias[j + 2 * u + 1]; }
             uint64_t w = pack_f32x2(w0, w1);
             if (kAct) { const uint64_t lk = fmul2(w, slope2); w = pack_f32x2(fmaxf(w0, f32x2_lo(lk)), fmaxf(w1, f32x2_hi(lk))); }   // LeakyReLU = max(x, 0.01 x)
             w = ffma2(gg[u], w, pack_f32x2(xr[j + 2 * u], xr[j + 2 * u + 1]));
@@ -85,15 +93,17 @@ __device__ __forceinline__ void chain_resid_chunk(uint32_t (&r)[32], const float
 }
 
 // first-layer mode: leaky(acc + bias + per-event bias) IS the residual row (feat_0, models/flow_model.py:224-228)
+template <bool kScaled = false>
 __device__ __forceinline__ void chain_first_chunk(uint32_t (&r)[32], const float* bias /*constant bank*/, bool staged, uint32_t rb_sm, const float* __restrict__ rb,
-                                                  uint64_t& s1, uint64_t& s2) {
+                                                  uint64_t& s1, uint64_t& s2, float ws = 1.f) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
         const float4 b4 = par_f4(staged, rb_sm + j * 4, rb + j);
         const float bb[4] = {bias[j] + b4.x, bias[j + 1] + b4.y, bias[j + 2] + b4.z, bias[j + 3] + b4.w};
 #pragma unroll
         for (int u = 0; u < 4; u += 2) {
-            const float w0 = leaky_relu(__uint_as_float(r[j + u]) + bb[u]), w1 = leaky_relu(__uint_as_float(r[j + u + 1]) + bb[u + 1]);
+            const float w0 = leaky_relu(kScaled ? fmaf(__uint_as_float(r[j + u]), ws, bb[u]) : __uint_as_float(r[j + u]) + bb[u]);
+            const float w1 = leaky_relu(kScaled ? fmaf(__uint_as_float(r[j + u + 1]), ws, bb[u + 1]) : __uint_as_float(r[j + u + 1]) + bb[u + 1]);
             const uint64_t w = pack_f32x2(w0, w1);
             s1 = fadd2(s1, w); s2 = ffma2(w, w, s2);
             r[j + u] = __float_as_uint(w0); r[j + u + 1] = __float_as_uint(w1);
@@ -133,6 +143,20 @@ __device__ __forceinline__ void chain_store_a(uint32_t a_addr, int rt, int col0,
                      "r"(pack16(v[8 * g], v[8 * g + 1], fp16)), "r"(pack16(v[8 * g + 2], v[8 * g + 3], fp16)),
                      "r"(pack16(v[8 * g + 4], v[8 * g + 5], fp16)), "r"(pack16(v[8 * g + 6], v[8 * g + 7], fp16)) : "memory");
 }
+// the same for the split mode: hi plane at a_addr, lo plane kChainABytes later
+__device__ __forceinline__ void chain_store_a_split(uint32_t a_addr, int rt, int col0, const float (&v)[32]) {
+    const uint32_t arow = a_addr + (uint32_t)((col0 >> 6) * 16384 + rt * 128);
+    const int cb = (col0 & 63) >> 3;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) split16(v[8 * g + 2 * u], v[8 * g + 2 * u + 1], hi[u], lo[u]);
+        const uint32_t a = arow + (uint32_t)(((cb + g) ^ (rt & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + kChainABytes), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+    }
+}
 __device__ __forceinline__ void sts_f2(uint32_t addr, float a, float b) { asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory"); }
 __device__ __forceinline__ float2 lds_f2(uint32_t addr) { float2 v; asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory"); return v; }
 
@@ -167,13 +191,17 @@ __device__ __forceinline__ void transpose_line_pieces(uint32_t (&a)[32], int lan
 #define CHAIN_STAMP(tile, k) do { } while (0)
 #endif
 
-template <bool kFp16, bool kFirst = false>
-__global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ ChainParams p) {
+template <bool kFp16, bool kFirst = false, bool kSplit = false>
+__global__ void __launch_bounds__(kChainThreads, kSplit ? 1 : 2) layer_chain_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a_lo,
+                                                                                    const __grid_constant__ ChainParams p) {
+    static_assert(!kSplit || kFp16, "the split (fp32-grade) mode runs on fp16 planes");
+    constexpr uint32_t kABytes = kSplit ? 2 * kChainABytes : kChainABytes;          // hi [| lo]
+    constexpr uint32_t kSlot = kSplit ? 2 * kChainSlotBytes : kChainSlotBytes;      // hi [| lo]
     extern __shared__ __align__(1024) uint8_t chain_smem[];      // no static smem in this kernel: the dynamic window starts 1024-aligned
     uint8_t* s_a = chain_smem;
     if ((smem_u32(s_a) & 1023u) != 0) __trap();
-    uint8_t* s_w = s_a + kChainABytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_w + kChainSlots * kChainSlotBytes);
+    uint8_t* s_w = s_a + kABytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_w + kChainSlots * kSlot);
     uint64_t* a_full = bars;             // TMA -> MMA      attention-output tile landed
     uint64_t* a_free = bars + 1;         // MMA -> TMA      last MMA of the tile retired: A may be overwritten
     uint64_t* w_full = bars + 2;         // [slots] TMA -> MMA
@@ -193,6 +221,7 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_a);
+        if (kSplit) prefetch_tmap(&tmap_a_lo);
         mbar_init(a_full, 1); mbar_init(a_free, 1);
         for (int i = 0; i < kChainSlots; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&epi_done[i], 4); }
@@ -213,9 +242,12 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                     if (j == (tile_i == 0 ? 0 : 2)) {                 // the A tile: first thing of the kernel, else after two weight slots of run-ahead
                         if (tile_i > 0) mbar_wait(a_free, (tile_i - 1) & 1);
                         CHAIN_STAMP(tile_i, 0);
-                        mbar_expect_tx(a_full, kKb0 * 16384);
+                        mbar_expect_tx(a_full, kKb0 * 16384 * (kSplit ? 2 : 1));
 #pragma unroll
-                        for (int kb = 0; kb < kKb0; ++kb) tma_load_2d(s_a + kb * 16384, &tmap_a, a_full, kb * 64, t * 128);
+                        for (int kb = 0; kb < kKb0; ++kb) {
+                            tma_load_2d(s_a + kb * 16384, &tmap_a, a_full, kb * 64, t * 128);
+                            if (kSplit) tma_load_2d(s_a + kChainABytes + kb * 16384, &tmap_a_lo, a_full, kb * 64, t * 128);
+                        }
                         CHAIN_STAMP(tile_i, 1);
                         if (!kFirst) {
                         // the fp32 residual tile of THIS tile (128 KB contiguous in the blocked layout) is first needed by the
@@ -231,8 +263,9 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                     else { const int jj = kFirst ? j + 2 : j; g = jj >> 3; nh = (jj >> 2) & 1; kb = jj & 3; }
                     const uint32_t s = slot_it % kChainSlots, ph = (slot_it / kChainSlots) & 1;
                     mbar_wait(&w_empty[s], ph ^ 1);
-                    mbar_expect_tx(&w_full[s], kChainSlotBytes);
-                    bulk_load(s_w + s * kChainSlotBytes, p.w[g] + (size_t)(kb * 256 + nh * 128) * 128, kChainSlotBytes, &w_full[s]);
+                    mbar_expect_tx(&w_full[s], kSlot);
+                    bulk_load(s_w + s * kSlot, p.w[g] + (size_t)(kb * 256 + nh * 128) * 128, kChainSlotBytes, &w_full[s]);
+                    if (kSplit) bulk_load(s_w + s * kSlot + kChainSlotBytes, p.w_lo[g] + (size_t)(kb * 256 + nh * 128) * 128, kChainSlotBytes, &w_full[s]);
                 }
             }
         }
@@ -255,11 +288,16 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                         mbar_wait(&w_full[s], ph);
                         tc_fence_after();
                         if (elect_one()) {
-                            const uint32_t a_addr = smem_u32(s_a + kb * 16384), b_addr = smem_u32(s_w + s * kChainSlotBytes);
+                            const uint32_t a_addr = smem_u32(s_a + kb * 16384), b_addr = smem_u32(s_w + s * kSlot);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)
+                            for (int k = 0; k < 4; ++k) {
                                 umma_bf16(tmem_base + nh * 128, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
                                           (uint32_t)((kb | k) != 0));
+                                if (kSplit) {      // hi.lo and lo.hi on the same accumulator
+                                    umma_bf16(tmem_base + nh * 128, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + kChainSlotBytes + k * 32), idesc, 1u);
+                                    umma_bf16(tmem_base + nh * 128, umma_desc_sw128(a_addr + kChainABytes + k * 32), umma_desc_sw128(b_addr + k * 32), idesc, 1u);
+                                }
+                            }
                             tc_commit(&w_empty[s]);
                             if (kb == kbn - 1) {
                                 tc_commit(&acc_full[nh]);
@@ -342,7 +380,7 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                     uint32_t r[32];
                     tmem_ld32(t_col + c * 32, r);
                     tmem_ld_wait();
-                    chain_resid_chunk<false>(r, xr, &p.cst[0][hh * 128 + c * 32], staged, psm + c * 128, p.gate_msa + eo + c * 32, s1p, s2p);
+                    chain_resid_chunk<false, kSplit>(r, xr, &p.cst[0][hh * 128 + c * 32], staged, psm + c * 128, p.gate_msa + eo + c * 32, s1p, s2p, p.wscale[0]);
                     if (valid) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 8) stg256_stream(xrow + (c * 4 + (j >> 3)) * 1024, &r[j]);
@@ -395,7 +433,7 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                         const uint64_t xh = ffma2(pack_f32x2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), rs2c, nm2c);
                         v[j] = f32x2_lo(xh); v[j + 1] = f32x2_hi(xh);
                     }
-                    chain_store_a(a_sh, rt, hh * 128 + c * 32, v, fp16);
+                    if (kSplit) chain_store_a_split(a_sh, rt, hh * 128 + c * 32, v); else chain_store_a(a_sh, rt, hh * 128 + c * 32, v, fp16);
                 }
                 stage_done(true);
             }
@@ -413,8 +451,8 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                     const float* b = &p.cst[1][hh * 128 + c * 32];
                     float v[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = leaky_relu(__uint_as_float(r[j]) + b[j]);
-                    chain_store_a(a_sh, rt, hh * 128 + c * 32, v, fp16);
+                    for (int j = 0; j < 32; ++j) v[j] = leaky_relu(kSplit ? fmaf(__uint_as_float(r[j]), p.wscale[1], b[j]) : __uint_as_float(r[j]) + b[j]);
+                    if (kSplit) chain_store_a_split(a_sh, rt, hh * 128 + c * 32, v); else chain_store_a(a_sh, rt, hh * 128 + c * 32, v, fp16);
                 }
                 stage_done(true);
             }
@@ -441,8 +479,8 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                     uint32_t r[32];
                     tmem_ld32(t_col + c * 32, r);
                     tmem_ld_wait();
-                    if (kFirst) chain_first_chunk(r, &p.cst[2][hh * 128 + c * 32], st2, psm + c * 128, p.row_bias + (size_t)evt * p.ld_row_bias + hh * 128 + c * 32, s1p, s2p);
-                    else chain_resid_chunk<true>(r, xr, &p.cst[2][hh * 128 + c * 32], st2, psm + c * 128, p.gate_mlp + eo + c * 32, s1p, s2p);
+                    if (kFirst) chain_first_chunk<kSplit>(r, &p.cst[2][hh * 128 + c * 32], st2, psm + c * 128, p.row_bias + (size_t)evt * p.ld_row_bias + hh * 128 + c * 32, s1p, s2p, p.wscale[0]);
+                    else chain_resid_chunk<true, kSplit>(r, xr, &p.cst[2][hh * 128 + c * 32], st2, psm + c * 128, p.gate_mlp + eo + c * 32, s1p, s2p, p.wscale[2]);
                     if (valid) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 8) stg256_stream(xrow + (c * 4 + (j >> 3)) * 1024, &r[j]);
@@ -482,7 +520,7 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                         float v[32];
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                        chain_store_a(a_sh, rt, hh * 128 + c * 32, v, fp16);
+                        if (kSplit) chain_store_a_split(a_sh, rt, hh * 128 + c * 32, v); else chain_store_a(a_sh, rt, hh * 128 + c * 32, v, fp16);
                     }
                 }
                 stage_done(next);
@@ -496,10 +534,11 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                     tc_fence_after();
                     // 64 columns (one 128-byte line per row) at a time: bias, pack, regroup across the 4 lanes of a group, store whole lines
                     const int row4 = t * 128 + (rt & ~3);                                   // first row of this lane's group of four
-                    uint16_t* dst = reinterpret_cast<uint16_t*>(p.qkv) + (size_t)row4 * (3 * kChainH) + g * kChainH + hh * 128 + (lane & 3) * 16;
+                    const size_t doff = (size_t)row4 * (3 * kChainH) + g * kChainH + hh * 128 + (lane & 3) * 16;
+                    uint16_t* dst = reinterpret_cast<uint16_t*>(p.qkv) + doff;
 #pragma unroll 1
                     for (int blk = 0; blk < 2; ++blk) {
-                        uint32_t a[32];
+                        uint32_t a[32], al[kSplit ? 32 : 1];
 #pragma unroll
                         for (int half = 0; half < 2; ++half) {
                             const int c = blk * 2 + half;
@@ -507,13 +546,24 @@ __global__ void __launch_bounds__(kChainThreads, 2) layer_chain_kernel(const __g
                             tmem_ld32(t_col + c * 32, r);
                             tmem_ld_wait();
                             const float* b = &p.cst[3 + g][hh * 128 + c * 32];
+                            const float ws = p.wscale[kFirst ? 1 + g : 3 + g];
 #pragma unroll
-                            for (int j = 0; j < 32; j += 2) a[half * 16 + (j >> 1)] = pack16(__uint_as_float(r[j]) + b[j], __uint_as_float(r[j + 1]) + b[j + 1], fp16);
+                            for (int j = 0; j < 32; j += 2) {
+                                if (kSplit) split16(fmaf(__uint_as_float(r[j]), ws, b[j]), fmaf(__uint_as_float(r[j + 1]), ws, b[j + 1]), a[half * 16 + (j >> 1)], al[kSplit ? half * 16 + (j >> 1) : 0]);
+                                else a[half * 16 + (j >> 1)] = pack16(__uint_as_float(r[j]) + b[j], __uint_as_float(r[j + 1]) + b[j + 1], fp16);
+                            }
                         }
                         transpose_line_pieces(a, lane);
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
                             if (row4 + i < p.M) stg256(dst + (size_t)i * (3 * kChainH) + blk * 64, &a[8 * i]);
+                        if constexpr (kSplit) {
+                            transpose_line_pieces(al, lane);
+                            uint16_t* dlo = reinterpret_cast<uint16_t*>(p.qkv_lo) + doff;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                if (row4 + i < p.M) stg256(dlo + (size_t)i * (3 * kChainH) + blk * 64, &al[8 * i]);
+                        }
                     }
                     stage_done(false);
                 }

@@ -161,6 +161,7 @@ struct EmbedTokParams {
     float* tok_feat; int ld;
     float* partial;
     void* tok_lp; int ld_lp; int lp_fp16;   // optional 16-bit copy (row pitch ld_lp): the feat_0 GEMM's A operand
+    void* tok_lp_lo;                        // split (fp32-grade) mode: low fp16 plane of that copy (val = hi + lo)
 };
 
 __global__ void __launch_bounds__(192) embed_tokens_kernel(EmbedTokParams p) {
@@ -265,7 +266,11 @@ __global__ void __launch_bounds__(192) embed_tokens_kernel(EmbedTokParams p) {
                 p.tok_feat[((size_t)(r0 - p.row0) + tok) * p.ld + col] = val;
                 if (p.tok_lp) {
                     const size_t o16 = ((size_t)(r0 - p.row0) + tok) * p.ld_lp + col;
-                    if (p.lp_fp16) reinterpret_cast<__half*>(p.tok_lp)[o16] = __float2half_rn(val);
+                    if (p.lp_fp16) {
+                        const __half hv = __float2half_rn(val);
+                        reinterpret_cast<__half*>(p.tok_lp)[o16] = hv;
+                        if (p.tok_lp_lo) reinterpret_cast<__half*>(p.tok_lp_lo)[o16] = __float2half_rn(val - __half2float(hv));
+                    }
                     else reinterpret_cast<__nv_bfloat16*>(p.tok_lp)[o16] = __float2bfloat16_rn(val);
                 }
                 colsum += val;

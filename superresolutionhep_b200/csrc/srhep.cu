@@ -96,7 +96,9 @@ struct Pass {
 struct SrhepHandle {
     int device = 0;
     SrhepDims d{};
-    int precision = SRHEP_PREC_FP32;
+    int precision = SRHEP_PREC_FP32;    // operand format of the kernels (split mode: SRHEP_PREC_FP16 planes)
+    int precision_req = SRHEP_PREC_FP32; // what srhep_create was asked for
+    bool split = false;                 // 'highest' on tensor cores: every 16-bit operand is an fp16 (hi, lo) pair, products run as hi.hi + hi.lo + lo.hi (kernels_chain.cuh, kernels_attn3.cuh)
     Layout L;
     std::string err;
     uint64_t launches = 0;
@@ -138,6 +140,7 @@ struct SrhepHandle {
     float *tok_feat = nullptr, *xres = nullptr, *qkv = nullptr, *h1buf = nullptr;
     void *act_a = nullptr, *act_b = nullptr;      // GEMM A operands (fp32 or bf16): ln_out / attn_out / mlp hidden / head in
     void *qkv_lp = nullptr;                        // bf16 q|k|v (SRHEP_PREC_BF16)
+    void *qkv_lo = nullptr, *act_b_lo = nullptr;   // split mode: low planes of q|k|v and of the attention output
     size_t cap_ws_rows = 0;
     // ODE state
     float *y_a = nullptr, *y_b = nullptr, *y_tmp = nullptr;
@@ -198,6 +201,11 @@ int dev_alloc(SrhepHandle* h, T*& p, size_t n) {
 }
 
 bool is_lp(const SrhepHandle* h) { return h->precision != SRHEP_PREC_FP32; }
+// the tcgen05 kernels the split (fp32-grade) mode is built from exist for the shipped architecture only
+bool split_supported(const SrhepDims& d) {
+    return d.h_dim == 256 && d.mlp_hid == 256 && d.heads > 0 && d.h_dim / d.heads == 64 && (d.cond + d.noisy_out + 63) / 64 * 64 == 192 &&
+           d.head_h1 == 128 && (d.v_in + d.ctx) % 64 == 0 && d.layers <= 64;
+}
 void read_switches(SrhepHandle* h) {
     auto on = [](const char* n) { const char* v = getenv(n); return v && *v && *v != '0'; };
     h->sw.no_chain = on("SRHEP_NO_CHAIN"); h->sw.no_chain_first = on("SRHEP_NO_CHAIN_FIRST"); h->sw.attn_simt = on("SRHEP_ATTN_SIMT"); h->sw.attn_v1 = on("SRHEP_ATTN_V1"); h->sw.attn_v2 = on("SRHEP_ATTN_V2");
@@ -368,7 +376,7 @@ struct Engine {
                 broadcast_prep_kernel<<<nE - 1, 128, 0, s>>>(b); check("broadcast_prep");
             }
         }
-        const bool embed_tc = lp && h->bw.embed_tc && !h->sw.no_embed_tc;
+        const bool embed_tc = lp && h->bw.embed_tc && !h->sw.no_embed_tc && !h->split;      // split mode: the fp32 CUDA-core embedding, planes written by its store
         if (M > 0 && embed_tc) {   // 2. per-cell embeddings on the tensor core (kernels_embed.cuh)
             EmbedTcParams q = *static_cast<const EmbedTcParams*>(h->bw.embed_tpl);
             q.M = M; q.row0 = p.r0; q.lp_fp16 = h->precision == SRHEP_PREC_FP16;
@@ -390,6 +398,7 @@ struct Engine {
             q.chunk_event = h->chunk_event; q.chunk_row = h->chunk_row; q.chunk_len = h->chunk_len;
             q.tok_feat = h->tok_feat; q.ld = ncol; q.partial = h->partial;
             q.tok_lp = lp ? (void*)h->bw.tok_lp : nullptr; q.ld_lp = h->bw.feat0_kpad; q.lp_fp16 = h->precision == SRHEP_PREC_FP16;
+            q.tok_lp_lo = h->split ? (void*)h->bw.tok_lp_lo : nullptr;
             if (!rc) { embed_tokens_kernel<<<std::min(p.c1 - p.c0, 148 * 8), 192, 0, s>>>(q); check("embed_tokens"); }
         }
         if (embed_tc) {   // 3. context from the cond columns of tok_feat
@@ -569,6 +578,11 @@ int alloc_workspace(SrhepHandle* h) {
     if (is_lp(h)) {
         if ((rc = re(h->qkv_lp, R * 3 * d.h_dim * 2))) return rc;
         CK(h, cudaMemset(h->qkv_lp, 0, R * 3 * d.h_dim * 2));    // rows past a pass's end are read (masked) by the attention tiles: keep them finite
+        if (h->split) {
+            if ((rc = re(h->qkv_lo, R * 3 * d.h_dim * 2))) return rc;
+            CK(h, cudaMemset(h->qkv_lo, 0, R * 3 * d.h_dim * 2));
+            if ((rc = re(h->act_b_lo, R * d.h_dim * 2))) return rc;
+        }
     }
     else { if ((rc = re(h->qkv, R * 3 * d.h_dim * sizeof(float)))) return rc; }
     h->cap_ws_rows = R;
@@ -699,7 +713,12 @@ int srhep_create(int device, const SrhepDims* dims, const float* weights_host, s
 
     SrhepHandle* h = new (std::nothrow) SrhepHandle();
     if (!h) return fail(nullptr, SRHEP_E_NOMEM, "host allocation failed");
-    h->device = device; h->d = *dims; h->precision = precision; h->L = L;
+    h->device = device; h->d = *dims; h->precision = h->precision_req = precision; h->L = L;
+    {   // fp32-grade arithmetic on the tensor cores unless the CUDA-core reference-order path is asked for (diagnostics, A/B tests)
+        const char* v = getenv("SRHEP_FP32_SIMT");
+        const bool simt = v && *v && *v != '0';
+        if (precision == SRHEP_PREC_FP32 && !simt && split_supported(*dims)) { h->split = true; h->precision = SRHEP_PREC_FP16; }
+    }
     const SrhepDims& d = h->d;
     h->mod_width = 6 * d.h_dim * d.layers + 2 * d.v_in;
     h->pass_tokens = 0;
@@ -750,7 +769,7 @@ int srhep_create(int device, const SrhepDims* dims, const float* weights_host, s
         CKC(cudaMalloc(&h->r1, r.size() * sizeof(float)));
         CKC(cudaMemcpy(h->r1, r.data(), r.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
-    if (precision != SRHEP_PREC_FP32) {
+    if (is_lp(h)) {
         rc = bf16_pack_weights(h, weights_host);
         if (rc) return cleanup(rc);
     }
@@ -771,7 +790,7 @@ int srhep_destroy(SrhepHandle* h) {
     drop_graphs(h);
     void* ptrs[] = {h->w, h->wqkv, h->bqkv, h->wmod, h->bmod, h->mod_tbias, h->r1, h->cu_dev, h->row_event, h->chunk_event, h->chunk_row, h->chunk_len,
                     h->ev_chunk_start, h->attn_work, h->temb, h->ev_a, h->ev_stats, h->layer_out, h->ctx, h->silu_ctx, h->mod, h->f0bias,
-                    h->partial, h->t_fill, h->tok_feat, h->xres, h->qkv, h->h1buf, h->act_a, h->act_b, h->qkv_lp, h->y_a, h->y_b, h->y_tmp,
+                    h->partial, h->t_fill, h->tok_feat, h->xres, h->qkv, h->h1buf, h->act_a, h->act_b, h->qkv_lp, h->qkv_lo, h->act_b_lo, h->y_a, h->y_b, h->y_tmp,
                     h->ybuf2, h->red_dev, h->sp_dev, h->stage_idx_dev, h->tap_layers, h->tap_feat0, h->tap_final};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (float* p : h->kbuf) if (p) cudaFree(p);
