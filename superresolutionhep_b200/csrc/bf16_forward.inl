@@ -112,7 +112,9 @@ int bf16_pack_weights(SrhepHandle* h, const float* wh) {
     // The velocity head ends in a 32-term dot product with cancellation: its operand rounding dominates the error of v (bf16 operands: rel-L2 2e-2
     // on v for 3e-3 on the transformer output).  Every head operand is a LayerNorm output or a weight, far inside fp16 range, so the fused
     // head runs on fp16 operands (8x finer mantissa, same tcgen05 rate) whatever the operand format of the transformer is.
-    pack_weight(img, bw.head1, wh + L.h1.w, hk, d.head_h1, hk, hk, 128, fp16 || bw.head_chain);
+    const float m_head1 = pow2_scale(wh + L.h1.w, hk, d.head_h1, hk);
+    bw.ws_head1 = 1.f / m_head1;
+    pack_weight(img, bw.head1, wh + L.h1.w, hk, d.head_h1, hk, hk, 128, fp16 || bw.head_chain, 0, m_head1);
     if (bw.head_chain) {
         pack_weight(img, bw.head2, wh + L.h2.w, kHeadH1, kHeadH2, kHeadH1, kHeadH1, kHeadH2, true);
         pack_weight(img, bw.head3, wh + L.h3.w, kHeadH2, kHeadH3, kHeadH2, kHeadH2, kHeadH3, true);
@@ -160,6 +162,7 @@ int bf16_pack_weights(SrhepHandle* h, const float* wh) {
             pack_weight(lo, bw.mlp1[l], wh + y.m1.w, H, H, H, H, 256, true, 1, m_m1[l]);
             pack_weight(lo, bw.mlp2[l], wh + y.m2.w, H, H, H, H, 256, true, 1, m_m2[l]);
         }
+        pack_weight(lo, bw.head1, wh + L.h1.w, hk, d.head_h1, hk, hk, 128, true, 1, m_head1);
         CK(h, cudaMalloc(&bw.img_lo, lo.size()));
         CK(h, cudaMemcpy(bw.img_lo, lo.data(), lo.size(), cudaMemcpyHostToDevice));
     }
@@ -202,7 +205,7 @@ int bf16_pack_weights(SrhepHandle* h, const float* wh) {
     CK(h, cudaFuncSetAttribute(attn3_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CK(h, cudaFuncSetAttribute(attn3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Att3Cfg<false>::kSmemBytes));
     CK(h, cudaFuncSetAttribute(attn3_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CK(h, cudaFuncSetAttribute(head_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeadSmemBytes));
+    CK(h, cudaFuncSetAttribute(head_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeadSmemBytes));
     CK(h, cudaFuncSetAttribute(layer_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemBytes));
     CK(h, cudaFuncSetAttribute(layer_chain_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CK(h, cudaFuncSetAttribute(layer_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemBytes));
@@ -216,6 +219,7 @@ int bf16_pack_weights(SrhepHandle* h, const float* wh) {
         CK(h, cudaFuncSetAttribute(layer_chain_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemBytesSplit));
         CK(h, cudaFuncSetAttribute(layer_chain_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemBytesSplit));
         CK(h, cudaFuncSetAttribute(attn3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Att3Cfg<true>::kSmemBytes));
+        CK(h, cudaFuncSetAttribute(head_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeadSmemBytesSplit));
     }
     return 0;
 }
@@ -253,6 +257,8 @@ int bf16_on_bind(SrhepHandle* h) {
         if ((rc = make_a_tmap(h, &bw.tm_tok_lo, bw.tok_lp_lo, R, bw.feat0_kpad, bw.feat0_kpad))) return rc;
         if ((rc = make_a_tmap(h, &bw.tm_qkv_lo, h->qkv_lo, R, 3 * d.h_dim, 3 * d.h_dim))) return rc;
         if ((rc = make_a_tmap(h, &bw.tm_kv64_lo, h->qkv_lo, R, 3 * d.h_dim, 3 * d.h_dim, kAtt2KvTile))) return rc;
+        // the head operand's low plane lives in the upper half of act_a (R x wide x 4 bytes; the high plane takes R x (v_in + ctx) x 2)
+        if ((rc = make_a_tmap(h, &bw.tm_hin_lo, (uint8_t*)h->act_a + R * (size_t)(d.v_in + d.ctx) * 2, R, d.v_in + d.ctx, d.v_in + d.ctx))) return rc;
     }
     return 0;
 }
@@ -273,6 +279,8 @@ void launch_gemm_bf16(Engine& E, const CUtensorMap& tm, int M, int K, int N, con
     gemm_bf16_kernel<BN, kLN><<<grid, kGemmThreads, gemm_bf16_smem_bytes<BN>(p.num_kb), E.s>>>(tm, p);
     E.check("gemm_bf16");
 }
+
+const float* wh_b1(SrhepHandle* h) { return h->bw.bias_h + h->bw.bias_head1; }      // host copy of the first head bias
 
 void launch_attn_bf16(Engine& E, const Pass& p, __nv_bfloat16* out) {
     if (E.rc || p.w1 == p.w0) return;
@@ -473,6 +481,22 @@ void bf16_forward(Engine& E, const Pass& p, const int* rev, const StageRef& st) 
     }
     E.cat = SRHEP_CAT_HEAD;
     const int hw = d.v_in + d.ctx;
+    const bool split_head = h->split && hw == kHeadK1 && d.head_h1 == kHeadH1 && !h->sw.head_fp32;
+    if (split_head) {      // first head GEMM on the tensor cores (hi / lo planes), LeakyReLU(h1 + b1) as fp32 rows; the tail follows on the CUDA cores
+        __half* hlo = (__half*)((uint8_t*)h->act_a + h->cap_ws_rows * (size_t)hw * 2);
+        E.head_prep<__half>(E.head_params(p, x), (__half*)a, hw, hlo);
+        if (!E.rc) {
+            HeadChainParams q{};
+            q.M = M; q.fp16 = 1; q.final_ln = d.head_final_ln;
+            q.w1 = bw.img + bw.head1; q.w1_lo = bw.img_lo + bw.head1; q.ws1 = bw.ws_head1; q.h1out = h->h1buf;
+            memcpy(q.b1, wh_b1(h), sizeof q.b1);
+            q.stage = st;
+            const int m_tiles = (M + 127) / 128;
+            head_chain_kernel<true><<<std::max(1, std::min(m_tiles, 148)), kHeadThreads, kHeadSmemBytesSplit, E.s>>>(bw.tm_hin, bw.tm_hin_lo, q);
+            E.check("head_chain_split");
+        }
+        E.head_done = false;
+    } else
     if (h->sw.head_fp32 || h->split) {
         E.head_prep<float>(E.head_params(p, x), (float*)h->act_a, hw);
         GemmEpilogue ep; ep.bias = E.W(L.h1.b); ep.act = 1;
@@ -491,7 +515,7 @@ void bf16_forward(Engine& E, const Pass& p, const int* rev, const StageRef& st) 
             memcpy(q.w4, bw.head_w4, sizeof q.w4); q.b4 = bw.head_b4;
             q.stage = st;
             const int m_tiles = (M + 127) / 128;
-            head_chain_kernel<<<std::max(1, std::min(m_tiles, 148)), kHeadThreads, kHeadSmemBytes, E.s>>>(bw.tm_hin, q);
+            head_chain_kernel<false><<<std::max(1, std::min(m_tiles, 148)), kHeadThreads, kHeadSmemBytes, E.s>>>(bw.tm_hin, bw.tm_hin, q);
             E.check("head_chain");
             E.head_done = true;
         }

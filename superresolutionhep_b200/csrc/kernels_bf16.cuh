@@ -957,7 +957,8 @@ struct Bf16Weights {
     uint8_t* img_lo = nullptr;
     float ws_feat0 = 1.f, ws_qkv[64][3], ws_out[64], ws_mlp1[64], ws_mlp2[64];     // 2^-s of each chain weight matrix (its images hold W * 2^s)
     __nv_bfloat16* tok_lp_lo = nullptr;
-    CUtensorMap tm_b_lo, tm_tok_lo, tm_qkv_lo, tm_kv64_lo;
+    CUtensorMap tm_b_lo, tm_tok_lo, tm_qkv_lo, tm_kv64_lo, tm_hin_lo;
+    float ws_head1 = 1.f;
 };
 
 }  // namespace srhep

@@ -730,15 +730,22 @@ __global__ void __launch_bounds__(256) head_prep_kernel(HeadPrepParams p, OutT* 
 // of the issue slots, almost all of it re-loading parameters).  Row i of the block's 64 = 8 i + warp: the 8 warps still cover 8
 // consecutive rows (256 contiguous bytes per column group of the blocked residual) in every iteration.
 template <typename OutT>
-__global__ void __launch_bounds__(256) head_prep_v4_kernel(HeadPrepParams p, OutT* hin, int ldh) {
+__global__ void __launch_bounds__(256) head_prep_v4_kernel(HeadPrepParams p, OutT* hin, int ldh, OutT* hin_lo = nullptr) {      // hin_lo: low fp16 plane (split mode)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool hc = lane < 24, hx1 = lane < 8;
     auto ld4 = [](const float* q) { return *reinterpret_cast<const float4*>(q); };
-    auto st4 = [](OutT* q, float4 v) {
+    auto st4 = [&](OutT* q, float4 v) {
         uint2 w;
         if (std::is_same<OutT, __half>::value) { __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w); w.x = *reinterpret_cast<uint32_t*>(&a); w.y = *reinterpret_cast<uint32_t*>(&b); }
         else { __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w); w.x = *reinterpret_cast<uint32_t*>(&a); w.y = *reinterpret_cast<uint32_t*>(&b); }
         *reinterpret_cast<uint2*>(q) = w;
+        if (std::is_same<OutT, __half>::value && hin_lo) {     // value = hi + lo
+            const __half2 a = *reinterpret_cast<const __half2*>(&w.x), b = *reinterpret_cast<const __half2*>(&w.y);
+            const float2 af = __half22float2(a), bf = __half22float2(b);
+            const __half2 la = __floats2half2_rn(v.x - af.x, v.y - af.y), lb = __floats2half2_rn(v.z - bf.x, v.w - bf.y);
+            uint2 wl; wl.x = *reinterpret_cast<const uint32_t*>(&la); wl.y = *reinterpret_cast<const uint32_t*>(&lb);
+            *reinterpret_cast<uint2*>(hin_lo + (q - hin)) = wl;
+        }
     };
     // packed f32x2 arithmetic (two columns per instruction): at the power cap the instruction count is what this kernel pays for
     auto P2 = [](float lo, float hi) { return (uint64_t)__float_as_uint(lo) | ((uint64_t)__float_as_uint(hi) << 32); };

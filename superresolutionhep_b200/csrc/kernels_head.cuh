@@ -28,6 +28,10 @@ constexpr uint32_t kHeadOffW3 = kHeadOffW2 + 16384;                 // 32 rows x
 constexpr uint32_t kHeadOffBars = kHeadOffW3 + 4096;
 constexpr size_t kHeadSmemBytes = kHeadOffBars + 256;
 constexpr int kHeadK1 = 512, kHeadH1 = 128, kHeadH2 = 64, kHeadH3 = 32;
+// split (fp32-grade) mode: only the first GEMM (K = 512, 90 % of the head's FLOPs) runs here, on (hi, lo) fp16 planes of hin and W1
+// (slot = hin hi | W1 hi | hin lo | W1 lo); LeakyReLU(h1 + b1) leaves as fp32 rows for the CUDA-core tail (head_tail_kernel)
+constexpr uint32_t kHeadSlotBytesSplit = 65536;
+constexpr size_t kHeadSmemBytesSplit = kHeadSlots * kHeadSlotBytesSplit + 256;
 
 struct HeadChainParams {
     int M; int fp16; int final_ln;
@@ -36,6 +40,8 @@ struct HeadChainParams {
     const uint8_t* w3;           // [32 rows x 128 B]
     float b1[kHeadH1], b2[kHeadH2], b3[kHeadH3], w4[kHeadH3]; float b4;
     StageRef stage;              // ODE stage: out / base / vout are pass-local rows
+    const uint8_t* w1_lo;        // split mode: low plane of W1 (images hold W1 * 2^s), 2^-s, and the fp32 output rows [M, 128]
+    float ws1; float* h1out;
 };
 
 __device__ __forceinline__ void ln_inplace_128(float (&v)[128]) {
@@ -51,7 +57,10 @@ __device__ __forceinline__ void ln_inplace_128(float (&v)[128]) {
     for (int j = 0; j < 128; ++j) v[j] = (v[j] - mean) * rstd;
 }
 
-__global__ void __launch_bounds__(kHeadThreads, 1) head_chain_kernel(const __grid_constant__ CUtensorMap tmap_hin, const __grid_constant__ HeadChainParams p) {
+template <bool kSplit = false>
+__global__ void __launch_bounds__(kHeadThreads, 1) head_chain_kernel(const __grid_constant__ CUtensorMap tmap_hin, const __grid_constant__ CUtensorMap tmap_hin_lo,
+                                                                     const __grid_constant__ HeadChainParams p) {
+    constexpr uint32_t kSlot = kSplit ? kHeadSlotBytesSplit : kHeadSlotBytes;
     extern __shared__ __align__(1024) uint8_t head_smem[];
     uint8_t* smem = head_smem;
     if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -59,7 +68,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_chain_kernel(const __gri
     uint8_t* s_a3 = smem + kHeadOffA3;
     uint8_t* s_w2 = smem + kHeadOffW2;
     uint8_t* s_w3 = smem + kHeadOffW3;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kHeadOffBars);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (kSplit ? kHeadSlots * kHeadSlotBytesSplit : kHeadOffBars));
     uint64_t* full = bars;               // [3] TMA -> MMA
     uint64_t* empty = bars + 3;          // [3] MMA -> TMA
     uint64_t* w23_full = bars + 6;
@@ -78,6 +87,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_chain_kernel(const __gri
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_hin);
+        if (kSplit) prefetch_tmap(&tmap_hin_lo);
         for (int i = 0; i < kHeadSlots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         mbar_init(w23_full, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(&acc1_full[i], 1); mbar_init(&acc1_empty[i], 4); }
@@ -92,17 +102,23 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_chain_kernel(const __gri
 
     if (warp == 0) {
         if (lane == 0) {
+            if (!kSplit) {
             mbar_expect_tx(w23_full, 16384 + 4096);
             bulk_load(s_w2, p.w2, 16384, w23_full);
             bulk_load(s_w3, p.w3, 4096, w23_full);
+            }
             uint32_t it = 0;
             for (int t = blockIdx.x; t < m_tiles; t += gridDim.x) {
                 for (int kb = 0; kb < kHeadK1 / 64; ++kb, ++it) {
                     const uint32_t s = it % kHeadSlots, ph = (it / kHeadSlots) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
-                    mbar_expect_tx(&full[s], kHeadSlotBytes);
-                    tma_load_2d(smem + s * kHeadSlotBytes, &tmap_hin, &full[s], kb * 64, t * 128);
-                    bulk_load(smem + s * kHeadSlotBytes + 16384, p.w1 + (size_t)kb * 16384, 16384, &full[s]);
+                    mbar_expect_tx(&full[s], kSlot);
+                    tma_load_2d(smem + s * kSlot, &tmap_hin, &full[s], kb * 64, t * 128);
+                    bulk_load(smem + s * kSlot + 16384, p.w1 + (size_t)kb * 16384, 16384, &full[s]);
+                    if (kSplit) {
+                        tma_load_2d(smem + s * kSlot + 32768, &tmap_hin_lo, &full[s], kb * 64, t * 128);
+                        bulk_load(smem + s * kSlot + 49152, p.w1_lo + (size_t)kb * 16384, 16384, &full[s]);
+                    }
                 }
             }
         }
@@ -118,21 +134,27 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_chain_kernel(const __gri
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint32_t a_addr = smem_u32(smem + s * kHeadSlotBytes), b_addr = a_addr + 16384;
+                    const uint32_t a_addr = smem_u32(smem + s * kSlot), b_addr = a_addr + 16384;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
+                    for (int k = 0; k < 4; ++k) {
                         umma_bf16(tmem_base + buf * 128, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc1, (uint32_t)((kb | k) != 0));
+                        if (kSplit) {
+                            umma_bf16(tmem_base + buf * 128, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + 32768 + k * 32), idesc1, 1u);
+                            umma_bf16(tmem_base + buf * 128, umma_desc_sw128(a_addr + 32768 + k * 32), umma_desc_sw128(b_addr + k * 32), idesc1, 1u);
+                        }
+                    }
                     tc_commit(&empty[s]);
                     if (kb == kHeadK1 / 64 - 1) tc_commit(&acc1_full[buf]);
                 }
                 __syncwarp();
             }
         };
-        mbar_wait(w23_full, 0);
+        if (!kSplit) mbar_wait(w23_full, 0);
         uint32_t j = 0;
         if (blockIdx.x < m_tiles) issue_g1(0);
         for (int t = blockIdx.x; t < m_tiles; t += gridDim.x, ++j) {
             if (t + (int)gridDim.x < m_tiles) issue_g1(j + 1);       // next tile's big GEMM runs under this tile's epilogues
+            if (kSplit) continue;                                     // the tail runs on the CUDA cores
             mbar_wait(a2_ready, j & 1);
             tc_fence_after();
             if (elect_one()) {
@@ -164,6 +186,26 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_chain_kernel(const __gri
             const int row = t * 128 + rt;
             const bool valid = row < p.M;
             const uint32_t buf = j & 1;
+            if constexpr (kSplit) {                                   // E1': LeakyReLU(h1 + b1) -> fp32 rows
+                mbar_wait(&acc1_full[buf], (j >> 1) & 1);
+                tc_fence_after();
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t r[32];
+                    tmem_ld32(t_lane + buf * 128 + c * 32, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(leaky_relu(fmaf(__uint_as_float(r[i]), p.ws1, p.b1[c * 32 + i])));
+                    if (valid) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 8) stg256(p.h1out + (size_t)row * kHeadH1 + c * 32 + i, &r[i]);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc1_empty[buf]);
+                continue;
+            }
             // ---------------------------------------------------------------- E1
             {
                 mbar_wait(&acc1_full[buf], (j >> 1) & 1);

@@ -326,16 +326,17 @@ struct Engine {
     }
 
     template <typename OutT>
-    void head_prep(const HeadPrepParams& q, OutT* hin, int ldh) {
+    void head_prep(const HeadPrepParams& q, OutT* hin, int ldh, OutT* hin_lo = nullptr) {
         if (rc || q.M <= 0) return;
         const SrhepDims& d = h->d;
         const int grid = (q.M + 7) / 8;
         const int ph = d.h_dim / 32, pc = d.cond / 32, px = d.ctx / 32;
         if (ph == 8 && pc == 3 && px == 5 && q.x_blocked && sizeof(OutT) == 2 && q.ldt % 4 == 0 && is_lp(h) && !h->sw.head_prep_scalar) {
-            head_prep_v4_kernel<OutT><<<(q.M + 63) / 64, 256, 0, s>>>(q, hin, ldh);
+            head_prep_v4_kernel<OutT><<<(q.M + 63) / 64, 256, 0, s>>>(q, hin, ldh, hin_lo);
             check("head_prep_v4");
             return;
         }
+        if (hin_lo) { rc = fail(h, SRHEP_E_INVALID, "head_prep: the split mode needs the float4 kernel's shapes"); return; }
         if (ph == 8 && pc == 3 && px == 5) head_prep_kernel<OutT, 8, 3, 5><<<grid, 256, 0, s>>>(q, hin, ldh);
         else if (ph == 2 && pc == 3 && px == 5) head_prep_kernel<OutT, 2, 3, 5><<<grid, 256, 0, s>>>(q, hin, ldh);
         else { rc = fail(h, SRHEP_E_INVALID, "head_prep: unsupported (h,cond,ctx)/32 = (%d,%d,%d)", ph, pc, px); return; }
