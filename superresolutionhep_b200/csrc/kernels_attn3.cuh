@@ -212,17 +212,34 @@ __global__ void __launch_bounds__(kAtt3Threads, kSplit ? 1 : 2) attn3_kernel(con
             __syncwarp();
         };
         const uint32_t idesc_o = umma_idesc_16(128, 64, fp16) | (1u << 16);                    // O = P V (V MN-major)
+        // The scores of a tile are issued one tile ahead of its softmax, ACROSS work items: S(first tile of item i + 1) goes out before
+        // P(last tile of item i) is awaited (its Q tile landed long ago), so the softmax warps find it ready after their epilogue.
+        bool first_issued = false;
+        AttnItem a_nx = (int)blockIdx.x < p.n_items ? p.items[blockIdx.x] : AttnItem{0, 0, 0, 0};
         for (int w = blockIdx.x; w < p.n_items; w += gridDim.x, ++item_i) {
-            const AttnItem a = p.items[w];
+            const AttnItem a = a_nx;
+            const bool has_next = w + (int)gridDim.x < p.n_items;
+            if (has_next) a_nx = p.items[w + gridDim.x];
             const int n_kv = (a.k_len + kAtt2KvTile - 1) / kAtt2KvTile;
             const uint32_t qb = item_i & 1;
             auto valid_of = [&](int j) { return min(kAtt2KvTile, a.k_len - j * kAtt2KvTile); };
-            mbar_wait(&q_full[qb], (item_i >> 1) & 1);
-            if (lane == 0) ATT_STAMP(item_i, 16);
-            issue_s(it, qb, valid_of(0), n_kv == 1);
-            if (lane == 0) ATT_STAMP(item_i, 17);
+            if (!first_issued) {
+                mbar_wait(&q_full[qb], (item_i >> 1) & 1);
+                if (lane == 0) ATT_STAMP(item_i, 16);
+                issue_s(it, qb, valid_of(0), n_kv == 1);
+                if (lane == 0) ATT_STAMP(item_i, 17);
+            }
+            first_issued = false;
             for (int j = 0; j < n_kv; ++j, ++it) {
                 if (j + 1 < n_kv) issue_s(it + 1, qb, valid_of(j + 1), j + 2 == n_kv);         // next tile's scores run under this tile's softmax
+                else if (has_next) {                                                           // ... and so do the first scores of the next item
+                    const int nkv2 = (a_nx.k_len + kAtt2KvTile - 1) / kAtt2KvTile;
+                    mbar_wait(&q_full[qb ^ 1], ((item_i + 1) >> 1) & 1);
+                    if (lane == 0) ATT_STAMP(item_i + 1, 16);
+                    issue_s(it + 1, qb ^ 1, min(kAtt2KvTile, a_nx.k_len), nkv2 == 1);
+                    if (lane == 0) ATT_STAMP(item_i + 1, 17);
+                    first_issued = true;
+                }
                 const uint32_t s = it % kStages, b = it & 1;
                 mbar_wait(&p_full[b], (it >> 1) & 1);
                 if (lane == 0) ATT_STAMP(item_i, 24 + j);
@@ -250,6 +267,49 @@ __global__ void __launch_bounds__(kAtt3Threads, kSplit ? 1 : 2) attn3_kernel(con
         const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
         constexpr int fp16 = kFp16 ? 1 : 0;
         uint32_t it = 0, item_i = 0;
+        // The epilogue of an item (O / l -> 16 bit -> global) is DEFERRED until the first key tile of the next item has been through the
+        // softmax: the last O += P V of the item retires meanwhile instead of being waited for with the SFU idle.  (The first tile of an item
+        // never touches O; the MMA warp holds the next item's first P V back until o_empty, which the deferred epilogue signals.)
+        bool pend = false; float pend_inv = 0.f; int pend_qrow = 0, pend_qlen = 0; uint32_t pend_it = 0;
+        auto epilogue = [&]() {
+            mbar_wait(&pv_done[(pend_it - 1) & 1], ((pend_it - 1) >> 1) & 1);
+            if (warp == 2 && lane == 0) ATT_STAMP(item_i, 48);
+            tc_fence_after();
+            const bool valid = row < pend_qlen;
+            __nv_bfloat16* orow = p.out + (size_t)(pend_qrow + row) * p.ldo + head * 64;
+            uint32_t o0[32], o1[32];
+            tmem_ld32(t_lane + Cfg::kColO, o0);
+            tmem_ld32(t_lane + Cfg::kColO + 32, o1);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(o_empty);
+            const float inv = pend_inv;
+            if (valid) {
+                uint32_t pk[32];
+                if constexpr (kSplit) {
+                    uint32_t pl[32];
+                    __nv_bfloat16* lrow = p.out_lo + (size_t)(pend_qrow + row) * p.ldo + head * 64;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        split16(__uint_as_float(o0[2 * i]) * inv, __uint_as_float(o0[2 * i + 1]) * inv, pk[i], pl[i]);
+                        split16(__uint_as_float(o1[2 * i]) * inv, __uint_as_float(o1[2 * i + 1]) * inv, pk[16 + i], pl[16 + i]);
+                    }
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) { stg256(orow + 16 * g, &pk[8 * g]); stg256(lrow + 16 * g, &pl[8 * g]); }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        pk[i] = pack16(__uint_as_float(o0[2 * i]) * inv, __uint_as_float(o0[2 * i + 1]) * inv, fp16);
+                        pk[16 + i] = pack16(__uint_as_float(o1[2 * i]) * inv, __uint_as_float(o1[2 * i + 1]) * inv, fp16);
+                    }
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) stg256(orow + 16 * g, &pk[8 * g]);
+                }
+            }
+            if (warp == 2 && lane == 0) ATT_STAMP(item_i, 49);
+            pend = false;
+        };
         // the descriptor of the NEXT item is fetched while this one is processed
         AttnItem a_next = (int)blockIdx.x < p.n_items ? p.items[blockIdx.x] : AttnItem{0, 0, 0, 0};
         for (int w = blockIdx.x; w < p.n_items; w += gridDim.x, ++item_i) {
@@ -261,6 +321,7 @@ __global__ void __launch_bounds__(kAtt3Threads, kSplit ? 1 : 2) attn3_kernel(con
             // keeps the barrier protocol going but does none of the arithmetic (its P rows stay whatever they were: rows are independent)
             const bool wact = q * 32 < a.q_len;
             if (!wact) {
+                if (pend) epilogue();
                 for (int j = 0; j < n_kv; ++j, ++it) {
                     const uint32_t b = it & 1;
                     mbar_wait(&s_full[b], (it >> 1) & 1);
@@ -304,45 +365,11 @@ __global__ void __launch_bounds__(kAtt3Threads, kSplit ? 1 : 2) attn3_kernel(con
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&p_full[b]);
                 if (warp == 2 && lane == 0) ATT_STAMP(item_i, 40 + j);
+                if (j == 0 && pend) epilogue();                            // the previous item's output, its last P V retired by now
             }
-            // epilogue: O / l -> 16 bit -> global
-            mbar_wait(&pv_done[(it - 1) & 1], ((it - 1) >> 1) & 1);
-            if (warp == 2 && lane == 0) ATT_STAMP(item_i, 48);
-            tc_fence_after();
-            const float inv = l > 0.f ? 1.f / l : 0.f;
-            const bool valid = row < a.q_len;
-            __nv_bfloat16* orow = p.out + (size_t)(a.q_row + row) * p.ldo + head * 64;
-            uint32_t o0[32], o1[32];
-            tmem_ld32(t_lane + Cfg::kColO, o0);
-            tmem_ld32(t_lane + Cfg::kColO + 32, o1);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(o_empty);
-            if (valid) {
-                uint32_t pk[32];
-                if constexpr (kSplit) {
-                    uint32_t pl[32];
-                    __nv_bfloat16* lrow = p.out_lo + (size_t)(a.q_row + row) * p.ldo + head * 64;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        split16(__uint_as_float(o0[2 * i]) * inv, __uint_as_float(o0[2 * i + 1]) * inv, pk[i], pl[i]);
-                        split16(__uint_as_float(o1[2 * i]) * inv, __uint_as_float(o1[2 * i + 1]) * inv, pk[16 + i], pl[16 + i]);
-                    }
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) { stg256(orow + 16 * g, &pk[8 * g]); stg256(lrow + 16 * g, &pl[8 * g]); }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        pk[i] = pack16(__uint_as_float(o0[2 * i]) * inv, __uint_as_float(o0[2 * i + 1]) * inv, fp16);
-                        pk[16 + i] = pack16(__uint_as_float(o1[2 * i]) * inv, __uint_as_float(o1[2 * i + 1]) * inv, fp16);
-                    }
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) stg256(orow + 16 * g, &pk[8 * g]);
-                }
-            }
-            if (warp == 2 && lane == 0) ATT_STAMP(item_i, 49);
+            pend = true; pend_inv = l > 0.f ? 1.f / l : 0.f; pend_qrow = a.q_row; pend_qlen = a.q_len; pend_it = it;
         }
+        if (pend) epilogue();
     }
     tc_fence_before();
     __syncthreads();
