@@ -31,7 +31,8 @@ Further legs on the same JSON line (``--no-extra`` skips them; none of them chan
 * ``pflow_sharded`` (configs[4]): SAPF forward with the real pf_hr weights over one shared list of SR-output-like events
                sharded by sharding.PFLOW_COST.
 * ``dopri5`` (N = 1): the reference's default solver (adaptive, atol = rtol = 1e-4) on the device, batch 20 and the
-               full batch, with the number of function evaluations.
+               full batch, with the number of function evaluations; in the benchmarked operand mode and in 'highest' (fp32-grade
+               on the tensor cores), which together with dopri5 is what ``inference.py`` runs when no flag is given.
 """
 from __future__ import annotations
 
@@ -606,29 +607,35 @@ def pflow_leg(args, world, rank, dev, barrier) -> dict:
 
 
 def dopri5_leg(args, dev) -> dict:
+    """The reference's real default: ``inference.py -p highest`` (fp32) + ``method="dopri5"`` (models/flow_model.py:303).  Both the
+    benchmarked 16-bit operand mode and the fp32-grade tensor-core mode ('highest') are timed."""
     from superresolutionhep_b200 import FlowModel
     cfg = flow_config(args.workload)
-    model = FlowModel(cfg, precision=args.precision)
-    model.load_state_dict(synthetic_state_dict(model.dims, seed=WEIGHT_SEED))
-    model.eval().cuda(dev)
     out = {"workload": f"{args.workload} SR sampling with the reference's default solver: dopri5, atol = rtol = 1e-4, n_steps={args.n_steps} output grid points; "
                        "the adaptive loop runs on the device as one conditional CUDA graph", "runs": []}
-    for B in (20, args.events):                                          # the shipped batch size (configs/single_e/inference_batch.yml:3) and the full batch
-        batch = synthetic_events(args.workload, B, seed=1234)
-        x0 = synthetic_noise(batch, seed=0).to(dev)
-        db = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in batch.items()}
-        model.generate_samples(db, n_steps=args.n_steps, method="dopri5", x0=x0)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 3
-        torch.cuda.synchronize(dev)
-        e0.record()
-        for _ in range(reps):
+    for prec in (args.precision, "fp32"):
+        model = FlowModel(cfg, precision=prec)
+        model.load_state_dict(synthetic_state_dict(model.dims, seed=WEIGHT_SEED))
+        model.eval().cuda(dev)
+        for B in (20, args.events):                                      # the shipped batch size (configs/single_e/inference_batch.yml:3) and the full batch
+            batch = synthetic_events(args.workload, B, seed=1234)
+            x0 = synthetic_noise(batch, seed=0).to(dev)
+            db = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in batch.items()}
             model.generate_samples(db, n_steps=args.n_steps, method="dopri5", x0=x0)
-        e1.record()
-        torch.cuda.synchronize(dev)
-        sec = e0.elapsed_time(e1) * 1e-3 / reps
-        out["runs"].append({"events": B, "events_s": B / sec, "seconds": sec, **model.last_stats})
-    model.release()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 3 if prec != "fp32" or B <= 64 else 1
+            torch.cuda.synchronize(dev)
+            e0.record()
+            for _ in range(reps):
+                model.generate_samples(db, n_steps=args.n_steps, method="dopri5", x0=x0)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            sec = e0.elapsed_time(e1) * 1e-3 / reps
+            out["runs"].append({"precision": prec + (" ('highest': fp32-grade on the tensor cores, hi/lo fp16 operand planes)" if prec == "fp32" else ""),
+                                "events": B, "events_s": B / sec, "seconds": sec, **model.last_stats})
+        model.release()
+        del model
+        torch.cuda.empty_cache()
     return out
 
 

@@ -10,6 +10,9 @@ from .config import SrDimsC
 
 _LIB: Optional[C.CDLL] = None
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsrhep.so")
+# the bounds-asserting debug build (nvcc -DSRHEP_BOUNDS: every global-memory index of the hot kernels is checked against the extent of its
+# buffer and traps with a message); selected with SRHEP_LIB_VARIANT=bounds in the environment of the process (tests/test_gpu_bounds.py)
+LIB_PATH_BOUNDS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsrhep_bounds.so")
 
 PREC_FP32, PREC_BF16, PREC_FP16 = 0, 1, 2
 METHODS = {"euler": 0, "midpoint": 1, "rk4": 2, "dopri5": 3}
@@ -65,11 +68,12 @@ def load() -> C.CDLL:
     global _LIB
     if _LIB is not None:
         return _LIB
-    if not os.path.isfile(LIB_PATH):
+    path = LIB_PATH_BOUNDS if os.environ.get("SRHEP_LIB_VARIANT") == "bounds" else LIB_PATH
+    if not os.path.isfile(path):
         raise RuntimeError(
-            f"{LIB_PATH} is missing: build it with `python -m superresolutionhep_b200.build` "
+            f"{path} is missing: build it with `python -m superresolutionhep_b200.build` "
             "(nvcc, sm_100a). This package has no CPU or PyTorch fallback path.")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     vp, i32, i64, u64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_float
     lib.srhep_version.restype = C.c_char_p
     lib.srhep_version.argtypes = []

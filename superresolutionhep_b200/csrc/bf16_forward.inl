@@ -290,6 +290,7 @@ void launch_attn_bf16(Engine& E, const Pass& p, __nv_bfloat16* out) {
     static_assert(sizeof(AttnItem) == sizeof(AttnWork), "work item layout");
     q.items = reinterpret_cast<const AttnItem*>(h->attn_work + p.w0); q.n_items = p.w1 - p.w0;
     q.out = out; q.out_lo = h->split ? (__nv_bfloat16*)h->act_b_lo : nullptr; q.ldo = d.h_dim; q.h_dim = d.h_dim;
+    q.ext.rows_cap = (int)h->cap_ws_rows; q.ext.n_events = h->B;
     q.scale_log2 = 1.4426950408889634f / sqrtf((float)(d.h_dim / d.heads));
     q.fp16 = h->precision == SRHEP_PREC_FP16;
     q.dbg = nullptr;
@@ -335,6 +336,10 @@ void launch_chain(Engine& E, int M, int l, const int* rev) {
     const float* ml = h->mod + (size_t)l * 6 * H;
     ChainParams q{};
     q.M = M; q.n_stages = last ? 3 : 6; q.fp16 = h->precision == SRHEP_PREC_FP16;
+    q.ext.rows_cap = (int)h->cap_ws_rows; q.ext.n_events = h->B;
+#ifdef SRHEP_BOUNDS
+    if (getenv("SRHEP_BOUNDS_SELFTEST")) q.ext.rows_cap = 1;      // tests/test_gpu_bounds.py: proves that a violated extent is caught (the kernel traps)
+#endif
     q.row_event = rev; q.x = h->xres;
     q.w[0] = bw.img + bw.out[l]; q.w[1] = bw.img + bw.mlp1[l]; q.w[2] = bw.img + bw.mlp2[l];
     const float* blh = bw.bias_h + l * bw.bias_layer_stride;
@@ -387,6 +392,7 @@ void launch_chain_first(Engine& E, int M, const int* rev) {
     const int H = d.h_dim;
     ChainParams q{};
     q.M = M; q.n_stages = 4; q.fp16 = h->precision == SRHEP_PREC_FP16;
+    q.ext.rows_cap = (int)h->cap_ws_rows; q.ext.n_events = h->B;
     q.row_event = rev; q.x = h->xres;
     q.w[0] = bw.img + bw.feat0;
     for (int j = 0; j < 3; ++j) q.w[1 + j] = bw.img + bw.qkv[0] + (size_t)j * H * H * 2;
@@ -487,7 +493,7 @@ void bf16_forward(Engine& E, const Pass& p, const int* rev, const StageRef& st) 
         E.head_prep<__half>(E.head_params(p, x), (__half*)a, hw, hlo);
         if (!E.rc) {
             HeadChainParams q{};
-            q.M = M; q.fp16 = 1; q.final_ln = d.head_final_ln;
+            q.M = M; q.fp16 = 1; q.final_ln = d.head_final_ln; q.ext.rows_cap = (int)h->cap_ws_rows; q.ext.n_events = h->B;
             q.w1 = bw.img + bw.head1; q.w1_lo = bw.img_lo + bw.head1; q.ws1 = bw.ws_head1; q.h1out = h->h1buf;
             memcpy(q.b1, wh_b1(h), sizeof q.b1);
             q.stage = st;
@@ -509,7 +515,7 @@ void bf16_forward(Engine& E, const Pass& p, const int* rev, const StageRef& st) 
     if (fused_head) {
         if (!E.rc) {
             HeadChainParams q;
-            q.M = M; q.fp16 = 1; q.final_ln = d.head_final_ln;
+            q.M = M; q.fp16 = 1; q.final_ln = d.head_final_ln; q.ext.rows_cap = (int)h->cap_ws_rows; q.ext.n_events = h->B;
             q.w1 = bw.img + bw.head1; q.w2 = bw.img + bw.head2; q.w3 = bw.img + bw.head3;
             memcpy(q.b1, bw.head_b1, sizeof q.b1); memcpy(q.b2, bw.head_b2, sizeof q.b2); memcpy(q.b3, bw.head_b3, sizeof q.b3);
             memcpy(q.w4, bw.head_w4, sizeof q.w4); q.b4 = bw.head_b4;

@@ -5,8 +5,19 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace srhep {
+
+// Bounds-asserting debug build (nvcc -DSRHEP_BOUNDS -> libsrhep_bounds.so, exercised by tests/test_gpu_bounds.py; compute-sanitizer is not
+// available on the GPU pool): every global-memory row / event index of the hot kernels is checked against the extent of its buffer, a
+// violation prints the site and traps, which the host sees as a launch failure.  Compiles to nothing in the production library.
+#ifdef SRHEP_BOUNDS
+#define SRHEP_CHECK(cond) do { if (!(cond)) { printf("srhep bounds violation %s:%d: %s (block %d thread %d)\n", __FILE__, __LINE__, #cond, (int)blockIdx.x, (int)threadIdx.x); __trap(); } } while (0)
+#else
+#define SRHEP_CHECK(cond) do { } while (0)
+#endif
+struct Extents { int rows_cap = 0; int n_events = 0; };      // rows of the pass workspace buffers; events of the binding (per-event arrays)
 
 constexpr float kLnEps = 1e-5f;      // nn.LayerNorm default eps (models/dense.py:62)
 constexpr float kLeaky = 0.01f;      // nn.LeakyReLU default slope

@@ -720,6 +720,7 @@ struct AttnBf16Params {
     float scale_log2;                 // log2(e) / sqrt(head_dim)
     int fp16;                         // 0 = bf16, 1 = fp16 operands / output
     long long* dbg;                   // optional timeline of CTA (0, 0): clock64 stamps, 64 per item, first 4 items; null in production
+    Extents ext;                      // checked in the -DSRHEP_BOUNDS build only
 };
 
 __global__ void __launch_bounds__(kAttnThreads, 2) attn_bf16_kernel(const __grid_constant__ CUtensorMap tmap_qkv, AttnBf16Params p) {

@@ -54,6 +54,7 @@ struct ChainParams {
     void* qkv;                   // [M, 768] 16-bit q|k|v of the next layer
     void* qkv_lo;                // split mode: its low plane
     long long* dbg;              // optional timeline of CTA 0 (clock64 stamps, 32 per tile, first 8 tiles); null in production
+    Extents ext;                 // checked in the -DSRHEP_BOUNDS build only
 };
 
 __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
@@ -335,8 +336,11 @@ __global__ void __launch_bounds__(kChainThreads, kSplit ? 1 : 2) layer_chain_ker
             const int ne = p.row_event[min(t * 128 + 127, p.M - 1)] - ev0 + 1;
             const bool staged = ne <= kChainStageEv;                   // CTA-uniform
             const int evt = valid ? p.row_event[row] : ev0;
+            SRHEP_CHECK(p.M <= p.ext.rows_cap && t * 128 + 127 < ((p.ext.rows_cap + 127) & ~127));      // TMA boxes and the blocked residual tile stay inside the workspace
+            SRHEP_CHECK(evt >= 0 && evt < p.ext.n_events && ev0 >= 0 && ev0 + ne <= p.ext.n_events);     // per-event adaLN rows
             const uint32_t xoff = (uint32_t)xblk_index(row, hh * 128);   // 32-bit element offsets keep the epilogue under its register budget
 #define xrow (p.x + xoff)                                         /* + 1024 floats per 8-column group (32 B pieces of this row) */
+            SRHEP_CHECK(!valid || (size_t)xoff + 15 * 1024 + 8 <= (size_t)((p.ext.rows_cap + 127) & ~127) * kChainH);      // last 32-byte piece of this thread's half row
             const uint32_t eo = (uint32_t)evt * (uint32_t)p.ld_mod + hh * 128;
             const uint32_t psm = par_sh + (uint32_t)(evt - ev0) * 3072 + hh * 512;       // this row's event, this thread's column half, array 0
             constexpr float inv_n = 1.0f / (float)kChainH;
@@ -556,7 +560,7 @@ __global__ void __launch_bounds__(kChainThreads, kSplit ? 1 : 2) layer_chain_ker
                         transpose_line_pieces(a, lane);
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
-                            if (row4 + i < p.M) stg256(dst + (size_t)i * (3 * kChainH) + blk * 64, &a[8 * i]);
+                            if (row4 + i < p.M) { SRHEP_CHECK(row4 + i < p.ext.rows_cap); stg256(dst + (size_t)i * (3 * kChainH) + blk * 64, &a[8 * i]); }
                         if constexpr (kSplit) {
                             transpose_line_pieces(al, lane);
                             uint16_t* dlo = reinterpret_cast<uint16_t*>(p.qkv_lo) + doff;

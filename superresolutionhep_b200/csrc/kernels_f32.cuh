@@ -656,6 +656,7 @@ struct HeadPrepParams {
     int M, h, cond;
     float* final_tap;                     // optional [Tp, h]: final_norm(x)
     int x_blocked;                        // x in the blocked residual layout (common.cuh: xblk_index)
+    Extents ext;                          // checked in the -DSRHEP_BOUNDS build only
 };
 
 template <typename OutT, int PH, int PC, int PX>     // per-lane counts: h/32, cond/32, ctx/32
@@ -800,6 +801,7 @@ __global__ void __launch_bounds__(256) head_prep_v4_kernel(HeadPrepParams p, Out
             ncc = hc ? ld4(p.tok_feat + (size_t)(row + 8) * p.ldt + c0) : z4;
             nev = p.row_event[row + 8];
         }
+        SRHEP_CHECK(row < p.ext.rows_cap && ev >= 0 && ev < p.ext.n_events);
         if (ev != ev_prev) {                                   // warp-uniform
             const float* cx = p.ctx + (size_t)ev * 160;
             x0 = ld4(cx + c0); x1 = hx1 ? ld4(cx + c1) : z4;

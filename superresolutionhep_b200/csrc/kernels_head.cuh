@@ -42,6 +42,7 @@ struct HeadChainParams {
     StageRef stage;              // ODE stage: out / base / vout are pass-local rows
     const uint8_t* w1_lo;        // split mode: low plane of W1 (images hold W1 * 2^s), 2^-s, and the fp32 output rows [M, 128]
     float ws1; float* h1out;
+    Extents ext;                 // checked in the -DSRHEP_BOUNDS build only
 };
 
 __device__ __forceinline__ void ln_inplace_128(float (&v)[128]) {
@@ -185,6 +186,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_chain_kernel(const __gri
         for (int t = blockIdx.x; t < m_tiles; t += gridDim.x, ++j) {
             const int row = t * 128 + rt;
             const bool valid = row < p.M;
+            SRHEP_CHECK(p.M <= p.ext.rows_cap && t * 128 + 127 < ((p.ext.rows_cap + 127) & ~127));
             const uint32_t buf = j & 1;
             if constexpr (kSplit) {                                   // E1': LeakyReLU(h1 + b1) -> fp32 rows
                 mbar_wait(&acc1_full[buf], (j >> 1) & 1);

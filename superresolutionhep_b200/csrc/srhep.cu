@@ -504,6 +504,7 @@ struct Engine {
         q.M = p.r1 - p.r0; q.h = d.h_dim; q.cond = d.cond;
         q.final_tap = h->debug ? h->tap_final : nullptr;
         q.x_blocked = x_blocked ? 1 : 0;
+        q.ext.rows_cap = (int)h->cap_ws_rows; q.ext.n_events = h->B;
         return q;
     }
 
@@ -683,7 +684,11 @@ int eval_all(SrhepHandle* h, cudaStream_t s, const float* x, float t, const floa
 // ========================================================================================
 extern "C" {
 
+#ifdef SRHEP_BOUNDS
+const char* srhep_version(void) { return "srhep 0.1 sm_100a bounds"; }      // the index-asserting debug build (common.cuh: SRHEP_CHECK)
+#else
 const char* srhep_version(void) { return "srhep 0.1 sm_100a"; }
+#endif
 
 size_t srhep_weight_count(const SrhepDims* dims) {
     if (!dims || dims->layers <= 0 || dims->layers > 1024) return 0;

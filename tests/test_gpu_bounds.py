@@ -1,0 +1,74 @@
+"""The bounds-asserting debug build (libsrhep_bounds.so, nvcc -DSRHEP_BOUNDS; superresolutionhep_b200/csrc/common.cuh: SRHEP_CHECK)
+on ragged cases.  compute-sanitizer is closed on the GPU pool, so the hot kernels carry their own index assertions: every row / event
+index they form is checked against the extent of its buffer.  Each case runs in its own process (a trap kills the CUDA context):
+
+* the checked library must run the ragged cases to the end and give bit-identical results to the production library
+  (the assertions do not touch the arithmetic);
+* with a deliberately wrong extent (SRHEP_BOUNDS_SELFTEST=1) the same run must die with the violation message: the checks are live.
+"""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+CASE = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, %(root)r)
+from superresolutionhep_b200 import FlowModel, _lib
+from superresolutionhep_b200.default_configs import flow_config
+from superresolutionhep_b200.synthetic import synthetic_events, synthetic_noise, synthetic_state_dict
+print("version", _lib.load().srhep_version().decode())
+out = {}
+for kind, counts in (("single_e", [1, 127, 128, 129, 804, 3, 260, 64]), ("multipart", [3280, 17, 640, 1, 1290])):
+    for prec in ("fp16", "bf16", "fp32"):
+        m = FlowModel(flow_config(kind), precision=prec); m.load_state_dict(synthetic_state_dict(m.dims, seed=7)); m.eval().cuda()
+        m.pass_tokens = 1500                      # several passes, one event larger than a pass
+        b = synthetic_events(kind, len(counts), seed=5, counts=np.array(counts)); x = synthetic_noise(b, seed=1)
+        db = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in b.items()}
+        xs = m.generate_samples(db, n_steps=3, method="midpoint", ret_seq=True, x0=x.cuda())
+        v = m(db, x.cuda(), torch.linspace(0.1, 0.9, len(counts)).cuda())
+        torch.cuda.synchronize()
+        assert torch.isfinite(xs).all() and torch.isfinite(v).all()
+        out[f"{kind}/{prec}/xs"] = xs.cpu(); out[f"{kind}/{prec}/v"] = v.cpu()
+        m.release()
+torch.save(out, sys.argv[1])
+print("done")
+"""
+
+
+def run_case(tmp_path, variant, selftest=False):
+    env = dict(os.environ)
+    env.pop("SRHEP_LIB_VARIANT", None)
+    env.pop("SRHEP_BOUNDS_SELFTEST", None)
+    if variant:
+        env["SRHEP_LIB_VARIANT"] = variant
+    if selftest:
+        env["SRHEP_BOUNDS_SELFTEST"] = "1"
+    out = str(tmp_path / f"out_{variant or 'prod'}_{int(selftest)}.pt")
+    r = subprocess.run([sys.executable, "-c", CASE % {"root": ROOT}, out], env=env, capture_output=True, text=True, timeout=600)
+    return r, out
+
+
+def test_bounds_checked_build_runs_ragged_cases_and_matches_production(tmp_path):
+    rb, fb = run_case(tmp_path, "bounds")
+    assert rb.returncode == 0, rb.stdout[-2000:] + rb.stderr[-2000:]
+    assert "version srhep 0.1 sm_100a bounds" in rb.stdout and "bounds violation" not in rb.stdout
+    rp, fp = run_case(tmp_path, None)
+    assert rp.returncode == 0, rp.stdout[-2000:] + rp.stderr[-2000:]
+    assert "bounds" not in rp.stdout.splitlines()[0]
+    a, b = torch.load(fb), torch.load(fp)
+    assert a.keys() == b.keys()
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+
+
+def test_bounds_checks_are_live(tmp_path):
+    r, _ = run_case(tmp_path, "bounds", selftest=True)
+    assert r.returncode != 0
+    assert "srhep bounds violation" in r.stdout + r.stderr
