@@ -35,8 +35,11 @@ extern "C" {
 #define SRHEP_E_STATE      -4   /* call order violated                  */
 
 /* arithmetic mode of the dense contractions (inference.py:330 `-p/--precision`):
- * FP32 = 'highest' (fp32 FFMA everywhere), BF16 = bf16 tcgen05 MMA operands with fp32
- * accumulation; LayerNorm statistics, softmax, residual stream and ODE state stay fp32. */
+ * FP32 = 'highest': fp32-grade on the tensor cores (every operand of a contraction is a pair of fp16 planes x = hi + lo,
+ * products run as hi.hi + hi.lo + lo.hi with fp32 accumulation; rel. error 2e-6 on the transformer output); the
+ * environment variable SRHEP_FP32_SIMT=1, read by srhep_create, selects reference-order fp32 FFMA on the CUDA cores instead.
+ * BF16 = bf16 tcgen05 MMA operands with fp32 accumulation.  In every mode LayerNorm statistics, softmax, residual
+ * stream and ODE state stay fp32. */
 #define SRHEP_PREC_FP32 0
 #define SRHEP_PREC_BF16 1
 #define SRHEP_PREC_FP16 2   /* as BF16 but fp16 tcgen05 operands: same speed, 8x finer mantissa; activations behind a

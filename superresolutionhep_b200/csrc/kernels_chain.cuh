@@ -29,10 +29,10 @@ constexpr int kChainThreads = 320;
 constexpr int kChainSlots = 3;
 constexpr uint32_t kChainSlotBytes = 16384;          // 128 weight rows x 128 B
 constexpr uint32_t kChainABytes = 65536;             // 4 k-blocks x (128 rows x 128 B)
-constexpr size_t kChainSmemBytes = kChainABytes + kChainSlots * kChainSlotBytes + 128;
+constexpr size_t kChainSmemBytes = kChainABytes + kChainSlots * kChainSlotBytes + 256;
 // split (fp32-grade) mode: every 16-bit operand is a pair of fp16 planes (hi, lo), each product runs as hi.hi + hi.lo + lo.hi
 // on the same fp32 accumulator (kernels_attn3.cuh: split16); the A buffer and the weight slots double, one CTA per SM
-constexpr size_t kChainSmemBytesSplit = 2 * kChainABytes + kChainSlots * 2 * kChainSlotBytes + 128;
+constexpr size_t kChainSmemBytesSplit = 2 * kChainABytes + kChainSlots * 2 * kChainSlotBytes + 256;
 constexpr int kChainH = 256;
 constexpr int kChainStageEv = 16;                    // events per tile whose adaLN rows are staged in shared memory (3 KB each, after the 4 KB statistics scratch)
 
@@ -55,6 +55,7 @@ struct ChainParams {
     void* qkv_lo;                // split mode: its low plane
     long long* dbg;              // optional timeline of CTA 0 (clock64 stamps, 32 per tile, first 8 tiles); null in production
     Extents ext;                 // checked in the -DSRHEP_BOUNDS build only
+    int a_early;                 // release the A buffer k-block by k-block (1 in production; 0 = after the tile's last MMA, for A/B runs)
 };
 
 __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
@@ -204,14 +205,15 @@ __global__ void __launch_bounds__(kChainThreads, kSplit ? 1 : 2) layer_chain_ker
     uint8_t* s_w = s_a + kABytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_w + kChainSlots * kSlot);
     uint64_t* a_full = bars;             // TMA -> MMA      attention-output tile landed
-    uint64_t* a_free = bars + 1;         // MMA -> TMA      last MMA of the tile retired: A may be overwritten
+    uint64_t* a_free = bars + 14;        // [4] MMA -> TMA  the tile's last MMAs over k-block kb of A retired: that k-block may be overwritten (the next
+                                         //     tile's A is requested k-block by k-block while the last stage still runs, not after it)
     uint64_t* w_full = bars + 2;         // [slots] TMA -> MMA
     uint64_t* w_empty = bars + 5;        // [slots] MMA -> TMA
     uint64_t* acc_full = bars + 8;       // [2] MMA -> epilogue  one 128-column half of a stage's accumulator complete
     uint64_t* epi_done = bars + 10;      // [2] epilogue -> MMA  the 4 warps of a column half are done with their half of TMEM
     uint64_t* a_written = bars + 12;     // epilogue -> MMA  all 8 warps rewrote the A operand (stages that feed another GEMM)
     uint64_t* par_full = bars + 13;      // bulk copies of the tile's per-event adaLN rows landed in the (dead) A buffer
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tiles = (p.M + 127) / 128;
@@ -223,7 +225,7 @@ __global__ void __launch_bounds__(kChainThreads, kSplit ? 1 : 2) layer_chain_ker
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_a);
         if (kSplit) prefetch_tmap(&tmap_a_lo);
-        mbar_init(a_full, 1); mbar_init(a_free, 1);
+        mbar_init(a_full, 1); for (int i = 0; i < 4; ++i) mbar_init(&a_free[i], 1);
         for (int i = 0; i < kChainSlots; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&epi_done[i], 4); }
         mbar_init(a_written, 8); mbar_init(par_full, 1);
@@ -241,11 +243,11 @@ __global__ void __launch_bounds__(kChainThreads, kSplit ? 1 : 2) layer_chain_ker
             for (int t = blockIdx.x; t < m_tiles; t += gridDim.x, ++tile_i) {
                 for (int j = 0; j < slots_per_tile; ++j, ++slot_it) {
                     if (j == (tile_i == 0 ? 0 : 2)) {                 // the A tile: first thing of the kernel, else after two weight slots of run-ahead
-                        if (tile_i > 0) mbar_wait(a_free, (tile_i - 1) & 1);
                         CHAIN_STAMP(tile_i, 0);
                         mbar_expect_tx(a_full, kKb0 * 16384 * (kSplit ? 2 : 1));
 #pragma unroll
                         for (int kb = 0; kb < kKb0; ++kb) {
+                            if (tile_i > 0) mbar_wait(&a_free[p.a_early ? kb : 3], (tile_i - 1) & 1);
                             tma_load_2d(s_a + kb * 16384, &tmap_a, a_full, kb * 64, t * 128);
                             if (kSplit) tma_load_2d(s_a + kChainABytes + kb * 16384, &tmap_a_lo, a_full, kb * 64, t * 128);
                         }
@@ -300,10 +302,8 @@ __global__ void __launch_bounds__(kChainThreads, kSplit ? 1 : 2) layer_chain_ker
                                 }
                             }
                             tc_commit(&w_empty[s]);
-                            if (kb == kbn - 1) {
-                                tc_commit(&acc_full[nh]);
-                                if (nh == 1 && g == p.n_stages - 1) tc_commit(a_free);
-                            }
+                            if (nh == 1 && g == p.n_stages - 1) tc_commit(&a_free[kb]);
+                            if (kb == kbn - 1) tc_commit(&acc_full[nh]);
                         }
                         __syncwarp();
                     }

@@ -16,6 +16,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>      // header-only NVTX 3: ranges cost nothing unless a tool (ncu --nvtx, nsys) is attached
+
 #include "kernels_f32.cuh"
 #include "kernels_bf16.cuh"
 #include "kernels_chain.cuh"
@@ -115,7 +117,7 @@ struct SrhepHandle {
     int mod_width = 0;
 
     // diagnostic switches (environment, read once per API call: A/B comparisons in the tests and tools)
-    struct Switches { bool no_chain = false, no_chain_first = false, attn_simt = false, attn_v1 = false, attn_v2 = false, no_lnfuse = false, head_fp32 = false, no_headchain = false, no_embed_tc = false, head_prep_scalar = false, chain_dbg = false, attn_dbg = false; int ctas_per_sm = 2; } sw;
+    struct Switches { bool no_chain = false, no_chain_first = false, attn_simt = false, attn_v1 = false, attn_v2 = false, no_lnfuse = false, head_fp32 = false, no_headchain = false, no_embed_tc = false, head_prep_scalar = false, chain_dbg = false, attn_dbg = false; int ctas_per_sm = 2; bool chain_a_early = true; } sw;
     // options
     int64_t pass_tokens = 0;
     int use_graph = 1;
@@ -211,6 +213,7 @@ void read_switches(SrhepHandle* h) {
     h->sw.no_chain = on("SRHEP_NO_CHAIN"); h->sw.no_chain_first = on("SRHEP_NO_CHAIN_FIRST"); h->sw.attn_simt = on("SRHEP_ATTN_SIMT"); h->sw.attn_v1 = on("SRHEP_ATTN_V1"); h->sw.attn_v2 = on("SRHEP_ATTN_V2");
     h->sw.no_lnfuse = on("SRHEP_NO_LNFUSE"); h->sw.head_fp32 = on("SRHEP_HEAD_FP32"); h->sw.no_headchain = on("SRHEP_NO_HEADCHAIN"); h->sw.no_embed_tc = on("SRHEP_NO_EMBED_TC"); h->sw.head_prep_scalar = on("SRHEP_HEAD_PREP_SCALAR");
     h->sw.chain_dbg = on("SRHEP_CHAIN_DBG"); h->sw.attn_dbg = on("SRHEP_ATTN_DBG");
+    { const char* v = getenv("SRHEP_CHAIN_A_EARLY"); h->sw.chain_a_early = !(v && *v == '0'); }
     { const char* v = getenv("SRHEP_CTAS_PER_SM"); h->sw.ctas_per_sm = (v && *v == '1') ? 1 : 2; }      // persistent grids of the chain / attention kernels: CTAs per SM
 }
 size_t act_elem_size(const SrhepHandle* h) { return is_lp(h) ? 2 : 4; }
@@ -246,6 +249,14 @@ int bf16_pack_weights(SrhepHandle* h, const float* weights_host);
 void bf16_free_weights(SrhepHandle* h);
 int bf16_on_bind(SrhepHandle* h);
 int64_t default_pass_tokens(int precision);
+
+// NVTX range over an API call / an evaluation / a kernel category (ncu --nvtx --nvtx-include "srhep_sample/" ...)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 struct Profiler {
     std::vector<cudaEvent_t> ev;       // ev[0] = start; ev[i+1] recorded after launch i
@@ -345,6 +356,7 @@ struct Engine {
 
     // One network evaluation for one pass (FlowModel.forward, models/flow_model.py:167-264).
     void enqueue_eval(const Pass& p, const StageRef& st) {
+        NvtxRange nvtx_eval("srhep_eval");
         const SrhepDims& d = h->d;
         const Layout& L = h->L;
         const int nE = p.e1 - p.e0, M = p.r1 - p.r0;
@@ -833,6 +845,7 @@ int srhep_set_debug(SrhepHandle* h, int enable) {
 }
 
 int srhep_bind_events(SrhepHandle* h, const SrhepCond* c, const int32_t* cu, int32_t B, void* stream) {
+    NvtxRange nvtx_api("srhep_bind_events");
     if (!h) return SRHEP_E_INVALID;
     if (!c || !cu || B < 0) return fail(h, SRHEP_E_INVALID, "null argument / negative event count");
     if (cu[0] != 0) return fail(h, SRHEP_E_INVALID, "cu_seqlens[0] must be 0");
@@ -925,6 +938,7 @@ int srhep_bind_events(SrhepHandle* h, const SrhepCond* c, const int32_t* cu, int
 }
 
 int srhep_velocity(SrhepHandle* h, const float* x, const float* t, float* v, void* stream) {
+    NvtxRange nvtx_api("srhep_velocity");
     if (!h) return SRHEP_E_INVALID;
     read_switches(h);
     if (!h->bound) return fail(h, SRHEP_E_STATE, "srhep_bind_events must be called first");
@@ -936,6 +950,7 @@ int srhep_velocity(SrhepHandle* h, const float* x, const float* t, float* v, voi
 
 int srhep_sample(SrhepHandle* h, const float* x0, const float* tg, int32_t n_steps, int32_t method, int32_t ret_seq,
                  float* x_seq, int32_t* nfe_out, void* stream) {
+    NvtxRange nvtx_api("srhep_sample");
     if (!h) return SRHEP_E_INVALID;
     read_switches(h);
     if (!h->bound) return fail(h, SRHEP_E_STATE, "srhep_bind_events must be called first");
@@ -1039,6 +1054,7 @@ int srhep_sample(SrhepHandle* h, const float* x0, const float* tg, int32_t n_ste
 // cells only (the reference's include the padded slots, SURVEY 7 "Solver semantics").
 int srhep_sample_dopri5(SrhepHandle* h, const float* x0, const float* tg, int32_t n_steps, float atol, float rtol,
                         int32_t ret_seq, float* x_seq, int32_t* stats_out, void* stream) {
+    NvtxRange nvtx_api("srhep_sample_dopri5");
     if (!h) return SRHEP_E_INVALID;
     read_switches(h);
     if (!h->bound) return fail(h, SRHEP_E_STATE, "srhep_bind_events must be called first");
