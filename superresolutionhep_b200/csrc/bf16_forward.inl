@@ -284,6 +284,7 @@ const float* wh_b1(SrhepHandle* h) { return h->bw.bias_h + h->bw.bias_head1; }  
 
 void launch_attn_bf16(Engine& E, const Pass& p, __nv_bfloat16* out) {
     if (E.rc || p.w1 == p.w0) return;
+    if (E.h->sw.only == 2 || E.h->sw.only == 3) return;
     SrhepHandle* h = E.h;
     const SrhepDims& d = h->d;
     AttnBf16Params q;
@@ -329,6 +330,7 @@ void launch_attn_bf16(Engine& E, const Pass& p, __nv_bfloat16* out) {
 // One launch for the row-local part of DiT layer l: out-projection ... q|k|v of layer l + 1 (kernels_chain.cuh)
 void launch_chain(Engine& E, int M, int l, const int* rev) {
     if (E.rc || M <= 0) return;
+    if (E.h->sw.only == 1 || E.h->sw.only == 3) return;
     SrhepHandle* h = E.h;
     const SrhepDims& d = h->d; Bf16Weights& bw = h->bw;
     const int H = d.h_dim;
@@ -436,7 +438,9 @@ void bf16_forward(Engine& E, const Pass& p, const int* rev, const StageRef& st) 
         else { ep.ln_w = bl + 5 * H; ep.ln_b = bl + 6 * H; ep.ln_shift = ml + 3 * H; ep.ln_scale = ml + 4 * H; }
     };
     const bool first_fused = chain && bw.feat0_kpad == 192 && (!h->sw.no_chain_first || h->split);
-    if (first_fused) launch_chain_first(E, M, rev);
+    const bool rest = h->sw.only == 0 || h->sw.only == 3;
+    if (!rest) { }
+    else if (first_fused) launch_chain_first(E, M, rev);
     else
     { GemmEpilogue ep; ep.row_bias = h->f0bias; ep.ld_row_bias = H; ep.row_event = rev; ep.act = 1;
       with_ln(ep, 0, false);
@@ -486,6 +490,7 @@ void bf16_forward(Engine& E, const Pass& p, const int* rev, const StageRef& st) 
         if (h->debug && h->tap_layers) E.tap(h->tap_layers + (size_t)l * h->cap_tap * H, x, M);
     }
     E.cat = SRHEP_CAT_HEAD;
+    if (!rest) { E.head_done = true; return; }
     const int hw = d.v_in + d.ctx;
     const bool split_head = h->split && hw == kHeadK1 && d.head_h1 == kHeadH1 && !h->sw.head_fp32;
     if (split_head) {      // first head GEMM on the tensor cores (hi / lo planes), LeakyReLU(h1 + b1) as fp32 rows; the tail follows on the CUDA cores

@@ -117,7 +117,7 @@ struct SrhepHandle {
     int mod_width = 0;
 
     // diagnostic switches (environment, read once per API call: A/B comparisons in the tests and tools)
-    struct Switches { bool no_chain = false, no_chain_first = false, attn_simt = false, attn_v1 = false, attn_v2 = false, no_lnfuse = false, head_fp32 = false, no_headchain = false, no_embed_tc = false, head_prep_scalar = false, chain_dbg = false, attn_dbg = false; int ctas_per_sm = 2; bool chain_a_early = true; } sw;
+    struct Switches { bool no_chain = false, no_chain_first = false, attn_simt = false, attn_v1 = false, attn_v2 = false, no_lnfuse = false, head_fp32 = false, no_headchain = false, no_embed_tc = false, head_prep_scalar = false, chain_dbg = false, attn_dbg = false; int ctas_per_sm = 2; bool chain_a_early = true; int only = 0; } sw;      // only: energy diagnostics (results wrong on purpose): 1 = launch the attention kernels only, 2 = the layer-chain kernels only, 3 = everything but those two
     // options
     int64_t pass_tokens = 0;
     int use_graph = 1;
@@ -214,6 +214,7 @@ void read_switches(SrhepHandle* h) {
     h->sw.no_lnfuse = on("SRHEP_NO_LNFUSE"); h->sw.head_fp32 = on("SRHEP_HEAD_FP32"); h->sw.no_headchain = on("SRHEP_NO_HEADCHAIN"); h->sw.no_embed_tc = on("SRHEP_NO_EMBED_TC"); h->sw.head_prep_scalar = on("SRHEP_HEAD_PREP_SCALAR");
     h->sw.chain_dbg = on("SRHEP_CHAIN_DBG"); h->sw.attn_dbg = on("SRHEP_ATTN_DBG");
     { const char* v = getenv("SRHEP_CHAIN_A_EARLY"); h->sw.chain_a_early = !(v && *v == '0'); }
+    { const char* v = getenv("SRHEP_ONLY"); h->sw.only = v ? atoi(v) : 0; }
     { const char* v = getenv("SRHEP_CTAS_PER_SM"); h->sw.ctas_per_sm = (v && *v == '1') ? 1 : 2; }      // persistent grids of the chain / attention kernels: CTAs per SM
 }
 size_t act_elem_size(const SrhepHandle* h) { return is_lp(h) ? 2 : 4; }
@@ -365,8 +366,9 @@ struct Engine {
         const int* rev = h->row_event + p.r0;
         const int ncol = d.cond + d.noisy_out;
 
+        const bool rest = h->sw.only == 0 || h->sw.only == 3;      // energy diagnostics: SRHEP_ONLY=1 / 2 launch the attention / chain kernels alone
         cat = SRHEP_CAT_EMBED;
-        {   // 1. per-event preparation
+        if (rest) {   // 1. per-event preparation
             EventPrepParams q;
             q.freqs = W(L.freqs); q.half = d.freq_dim / 2;
             q.wt0 = W(L.t0.w); q.bt0 = W(L.t0.b); q.wt2 = W(L.t2.w); q.bt2 = W(L.t2.b); q.t_emb = d.t_emb;
@@ -390,6 +392,7 @@ struct Engine {
             }
         }
         const bool embed_tc = lp && h->bw.embed_tc && !h->sw.no_embed_tc && !h->split;      // split mode: the fp32 CUDA-core embedding, planes written by its store
+        if (!rest) { if (M > 0 && lp) bf16_forward(*this, p, rev, st); return; }
         if (M > 0 && embed_tc) {   // 2. per-cell embeddings on the tensor core (kernels_embed.cuh)
             EmbedTcParams q = *static_cast<const EmbedTcParams*>(h->bw.embed_tpl);
             q.M = M; q.row0 = p.r0; q.lp_fp16 = h->precision == SRHEP_PREC_FP16;
