@@ -337,7 +337,7 @@ void launch_chain(Engine& E, int M, int l, const int* rev) {
     const bool last = l + 1 == d.layers;
     const float* ml = h->mod + (size_t)l * 6 * H;
     ChainParams q{};
-    q.M = M; q.n_stages = last ? 3 : 6; q.fp16 = h->precision == SRHEP_PREC_FP16; q.a_early = h->sw.chain_a_early;
+    q.M = M; q.n_stages = last ? 3 : 6; q.fp16 = h->precision == SRHEP_PREC_FP16; q.a_early = h->sw.chain_a_early; q.ln_direct = h->sw.chain_ln_direct;
     q.ext.rows_cap = (int)h->cap_ws_rows; q.ext.n_events = h->B;
 #ifdef SRHEP_BOUNDS
     if (getenv("SRHEP_BOUNDS_SELFTEST")) q.ext.rows_cap = 1;      // tests/test_gpu_bounds.py: proves that a violated extent is caught (the kernel traps)
@@ -393,7 +393,7 @@ void launch_chain_first(Engine& E, int M, const int* rev) {
     const SrhepDims& d = h->d; Bf16Weights& bw = h->bw;
     const int H = d.h_dim;
     ChainParams q{};
-    q.M = M; q.n_stages = 4; q.fp16 = h->precision == SRHEP_PREC_FP16; q.a_early = h->sw.chain_a_early;
+    q.M = M; q.n_stages = 4; q.fp16 = h->precision == SRHEP_PREC_FP16; q.a_early = h->sw.chain_a_early; q.ln_direct = h->sw.chain_ln_direct;
     q.ext.rows_cap = (int)h->cap_ws_rows; q.ext.n_events = h->B;
     q.row_event = rev; q.x = h->xres;
     q.w[0] = bw.img + bw.feat0;

@@ -56,6 +56,7 @@ struct ChainParams {
     long long* dbg;              // optional timeline of CTA 0 (clock64 stamps, 32 per tile, first 8 tiles); null in production
     Extents ext;                 // checked in the -DSRHEP_BOUNDS build only
     int a_early;                 // release the A buffer k-block by k-block (1 in production; 0 = after the tile's last MMA, for A/B runs)
+    int ln_direct;               // stage 2: LayerNorm output straight to A (1 in production; 0 = parked in TMEM and copied in a third pass, for A/B runs)
 };
 
 __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
@@ -158,6 +159,15 @@ __device__ __forceinline__ void chain_store_a_split(uint32_t a_addr, int rt, int
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + kChainABytes), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
     }
+}
+// 16 already packed pairs (32 consecutive columns of row `rt`) -> the A buffer
+__device__ __forceinline__ void chain_store_a_packed(uint32_t a_addr, int rt, int col0, const uint32_t* pk) {
+    const uint32_t arow = a_addr + (uint32_t)((col0 >> 6) * 16384 + rt * 128);
+    const int cb = (col0 & 63) >> 3;
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(arow + (uint32_t)(((cb + g) ^ (rt & 7)) << 4)),
+                     "r"(pk[4 * g]), "r"(pk[4 * g + 1]), "r"(pk[4 * g + 2]), "r"(pk[4 * g + 3]) : "memory");
 }
 __device__ __forceinline__ void sts_f2(uint32_t addr, float a, float b) { asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory"); }
 __device__ __forceinline__ float2 lds_f2(uint32_t addr) { float2 v; asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory"); return v; }
@@ -505,6 +515,40 @@ __global__ void __launch_bounds__(kChainThreads, kSplit ? 1 : 2) layer_chain_ker
                     const float rstd = rsqrtf(fmaxf((s2 + o1.y) * inv_n - mean * mean, 0.f) + kLnEps);
                     const uint64_t rs2 = pack_f32x2(rstd, rstd), nm2 = pack_f32x2(-mean * rstd, -mean * rstd);
                     uint64_t t1p = 0ull, t2p = 0ull;
+                    // Tensor-memory reads are the resource the two CTAs of an SM share (57 B per clock and SM, tools/micro/ldtm_bw.cu), so the
+                    // LayerNorm output goes STRAIGHT to the A operand instead of being parked in TMEM and copied in a third pass.  The scratch
+                    // and the staged adaLN rows of up to four events live in k-block 0 of the A buffer (columns 0-63, bytes 0 .. 16 KB) and are
+                    // still being read by other threads: the threads that own those columns keep their 64 packed values in registers until the
+                    // barrier; every other column is written at once.
+                    const bool direct = !kSplit && ne <= 4 && p.ln_direct;      // CTA-uniform
+                    if (direct) {
+#pragma unroll 1
+                        for (int c = 2; c < 4; ++c) {                    // columns that nobody else is reading: straight to A
+                            uint32_t r[32];
+                            tmem_ld32(t_col + c * 32, r);
+                            tmem_ld_wait();
+                            chain_ln_mod_chunk(r, rs2, nm2, &p.cst[8][hh * 128 + c * 32], &p.cst[9][hh * 128 + c * 32], staged, psm + 1024 + c * 128, psm + 2048 + c * 128,
+                                               p.scale_nxt + eo + c * 32, p.shift_nxt + eo + c * 32, t1p, t2p);
+                            uint32_t pk[16];
+#pragma unroll
+                            for (int j = 0; j < 32; j += 2) pk[j >> 1] = pack16(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), fp16);
+                            chain_store_a_packed(a_sh, rt, hh * 128 + c * 32, pk);
+                        }
+                        uint32_t held[32];
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {                    // columns [hh * 128, hh * 128 + 64): k-block 0 for the hh = 0 threads, processed last so that little else is live
+                            uint32_t r[32];
+                            tmem_ld32(t_col + c * 32, r);
+                            tmem_ld_wait();
+                            chain_ln_mod_chunk(r, rs2, nm2, &p.cst[8][hh * 128 + c * 32], &p.cst[9][hh * 128 + c * 32], staged, psm + 1024 + c * 128, psm + 2048 + c * 128,
+                                               p.scale_nxt + eo + c * 32, p.shift_nxt + eo + c * 32, t1p, t2p);
+#pragma unroll
+                            for (int j = 0; j < 32; j += 2) held[c * 16 + (j >> 1)] = pack16(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), fp16);
+                            if (hh != 0) chain_store_a_packed(a_sh, rt, hh * 128 + c * 32, &held[c * 16]);
+                        }
+                        named_bar_sync(1, 256);                          // all reads of the scratch and the staged rows are done: k-block 0 may be rewritten
+                        if (hh == 0) { chain_store_a_packed(a_sh, rt, 0, &held[0]); chain_store_a_packed(a_sh, rt, 32, &held[16]); }
+                    } else {
 #pragma unroll 1
                     for (int c = 0; c < 4; ++c) {                        // next layer's LN1 affine + modulate, parked in TMEM (the staged rows are still being read)
                         uint32_t r[32];
@@ -525,6 +569,7 @@ __global__ void __launch_bounds__(kChainThreads, kSplit ? 1 : 2) layer_chain_ker
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
                         if (kSplit) chain_store_a_split(a_sh, rt, hh * 128 + c * 32, v); else chain_store_a(a_sh, rt, hh * 128 + c * 32, v, fp16);
+                    }
                     }
                 }
                 stage_done(next);

@@ -117,7 +117,7 @@ struct SrhepHandle {
     int mod_width = 0;
 
     // diagnostic switches (environment, read once per API call: A/B comparisons in the tests and tools)
-    struct Switches { bool no_chain = false, no_chain_first = false, attn_simt = false, attn_v1 = false, attn_v2 = false, no_lnfuse = false, head_fp32 = false, no_headchain = false, no_embed_tc = false, head_prep_scalar = false, chain_dbg = false, attn_dbg = false; int ctas_per_sm = 2; bool chain_a_early = true; int only = 0; } sw;      // only: energy diagnostics (results wrong on purpose): 1 = launch the attention kernels only, 2 = the layer-chain kernels only, 3 = everything but those two
+    struct Switches { bool no_chain = false, no_chain_first = false, attn_simt = false, attn_v1 = false, attn_v2 = false, no_lnfuse = false, head_fp32 = false, no_headchain = false, no_embed_tc = false, head_prep_scalar = false, chain_dbg = false, attn_dbg = false; int ctas_per_sm = 2; bool chain_a_early = true, chain_ln_direct = true; int only = 0; } sw;      // only: energy diagnostics (results wrong on purpose): 1 = launch the attention kernels only, 2 = the layer-chain kernels only, 3 = everything but those two
     // options
     int64_t pass_tokens = 0;
     int use_graph = 1;
@@ -213,7 +213,7 @@ void read_switches(SrhepHandle* h) {
     h->sw.no_chain = on("SRHEP_NO_CHAIN"); h->sw.no_chain_first = on("SRHEP_NO_CHAIN_FIRST"); h->sw.attn_simt = on("SRHEP_ATTN_SIMT"); h->sw.attn_v1 = on("SRHEP_ATTN_V1"); h->sw.attn_v2 = on("SRHEP_ATTN_V2");
     h->sw.no_lnfuse = on("SRHEP_NO_LNFUSE"); h->sw.head_fp32 = on("SRHEP_HEAD_FP32"); h->sw.no_headchain = on("SRHEP_NO_HEADCHAIN"); h->sw.no_embed_tc = on("SRHEP_NO_EMBED_TC"); h->sw.head_prep_scalar = on("SRHEP_HEAD_PREP_SCALAR");
     h->sw.chain_dbg = on("SRHEP_CHAIN_DBG"); h->sw.attn_dbg = on("SRHEP_ATTN_DBG");
-    { const char* v = getenv("SRHEP_CHAIN_A_EARLY"); h->sw.chain_a_early = !(v && *v == '0'); }
+    { const char* v = getenv("SRHEP_CHAIN_A_EARLY"); h->sw.chain_a_early = !(v && *v == '0'); v = getenv("SRHEP_CHAIN_LN_DIRECT"); h->sw.chain_ln_direct = !(v && *v == '0'); }
     { const char* v = getenv("SRHEP_ONLY"); h->sw.only = v ? atoi(v) : 0; }
     { const char* v = getenv("SRHEP_CTAS_PER_SM"); h->sw.ctas_per_sm = (v && *v == '1') ? 1 : 2; }      // persistent grids of the chain / attention kernels: CTAs per SM
 }
