@@ -68,7 +68,8 @@ def load() -> C.CDLL:
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = LIB_PATH_BOUNDS if os.environ.get("SRHEP_LIB_VARIANT") == "bounds" else LIB_PATH
+    variant = os.environ.get("SRHEP_LIB_VARIANT")          # "bounds": the index-asserting build; any other name: libsrhep_<name>.so next to it (A/B builds)
+    path = LIB_PATH_BOUNDS if variant == "bounds" else (os.path.join(os.path.dirname(LIB_PATH), f"libsrhep_{variant}.so") if variant else LIB_PATH)
     if not os.path.isfile(path):
         raise RuntimeError(
             f"{path} is missing: build it with `python -m superresolutionhep_b200.build` "
