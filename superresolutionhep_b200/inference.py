@@ -19,7 +19,8 @@ What is different, and why:
   branch, keyed ``"<Tree>/<branch>"``.  Neither package is installable in the build image, so only the fall-back is tested;
 * keys that the shipped single_e YAMLs do not define but the reference reads (``store_ensemble_components``,
   ``store_energy_incidence``, ``max_particles``: SURVEY.md Appendix D) default to False / False / 4 instead of raising;
-* ``-p/--precision`` selects the arithmetic of the sm_100a path: ``highest`` = fp32 kernels, ``high`` / ``medium`` = fp16
+* ``-p/--precision`` selects the arithmetic of the sm_100a path: ``highest`` = fp32-grade arithmetic on the tensor cores (every operand a
+  pair of fp16 planes, fp32 accumulation; rel. error 2e-6 against the fp32 reference), ``high`` / ``medium`` = fp16
   tcgen05 operands with fp32 accumulation (the reference passes the same string to ``torch.set_float32_matmul_precision``, inference.py:346,374).
 """
 from __future__ import annotations
