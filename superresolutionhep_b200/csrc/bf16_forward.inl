@@ -206,6 +206,7 @@ int bf16_pack_weights(SrhepHandle* h, const float* wh) {
     CK(h, cudaFuncSetAttribute(attn3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Att3Cfg<false>::kSmemBytes));
     CK(h, cudaFuncSetAttribute(attn3_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CK(h, cudaFuncSetAttribute(head_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeadSmemBytes));
+    CK(h, cudaFuncSetAttribute(head_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHFSmemBytes));
     CK(h, cudaFuncSetAttribute(layer_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemBytes));
     CK(h, cudaFuncSetAttribute(layer_chain_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CK(h, cudaFuncSetAttribute(layer_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemBytes));
@@ -514,6 +515,26 @@ void bf16_forward(Engine& E, const Pass& p, const int* rev, const StageRef& st) 
         E.gemm_f32<float>((float*)h->act_a, hw, E.W(L.h1.w), hw, h->h1buf, d.head_h1, M, d.head_h1, hw, ep);
     } else {
     const bool fused_head = bw.head_chain && !h->sw.no_headchain;
+    // the whole head in ONE kernel (kernels_head_fused.cuh): the preparation warps write the operand rows straight into shared memory
+    const bool one_kernel = fused_head && !h->sw.no_head_fused && !h->sw.head_prep_scalar && !h->sw.head_prep_v4 && !(h->debug && h->tap_final) && E.x_blocked &&
+                            d.h_dim == 256 && d.cond == 96 && d.ctx == 160 && (d.cond + d.noisy_out) % 4 == 0;
+    if (one_kernel) {
+        if (!E.rc) {
+            HeadFusedParams f{};
+            f.q = E.head_params(p, x);
+            HeadChainParams& q = f.c;
+            q.M = M; q.fp16 = 1; q.final_ln = d.head_final_ln; q.ext.rows_cap = (int)h->cap_ws_rows; q.ext.n_events = h->B;
+            q.w1 = bw.img + bw.head1; q.w2 = bw.img + bw.head2; q.w3 = bw.img + bw.head3;
+            memcpy(q.b1, bw.head_b1, sizeof q.b1); memcpy(q.b2, bw.head_b2, sizeof q.b2); memcpy(q.b3, bw.head_b3, sizeof q.b3);
+            memcpy(q.w4, bw.head_w4, sizeof q.w4); q.b4 = bw.head_b4;
+            q.stage = st;
+            { const char* v = getenv("SRHEP_HF_DIAG"); f.diag = v ? atoi(v) : 0; }
+            const int m_tiles = (M + 127) / 128;
+            head_fused_kernel<<<std::max(1, std::min(m_tiles, 148)), kHFThreads, kHFSmemBytes, E.s>>>(f);
+            E.check("head_fused");
+            E.head_done = true;
+        }
+    } else {
     if (fp16 || fused_head) E.head_prep<__half>(E.head_params(p, x), (__half*)a, hw);
     else E.head_prep<__nv_bfloat16>(E.head_params(p, x), a, hw);
     E.head_done = false;
@@ -533,5 +554,6 @@ void bf16_forward(Engine& E, const Pass& p, const int* rev, const StageRef& st) 
     } else
     { GemmEpilogue ep; ep.bias = bw.bias + bw.bias_head1; ep.act = 1;
       launch_gemm_bf16<128>(E, bw.tm_hin, M, hw, d.head_h1, bw.img + bw.head1, h->h1buf, d.head_h1, 0, ep); }
+    }
     }
 }

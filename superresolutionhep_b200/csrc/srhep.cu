@@ -22,6 +22,7 @@
 #include "kernels_bf16.cuh"
 #include "kernels_chain.cuh"
 #include "kernels_head.cuh"
+#include "kernels_head_fused.cuh"
 #include "kernels_attn.cuh"
 #include "kernels_attn3.cuh"
 #include "kernels_embed.cuh"
@@ -117,7 +118,7 @@ struct SrhepHandle {
     int mod_width = 0;
 
     // diagnostic switches (environment, read once per API call: A/B comparisons in the tests and tools)
-    struct Switches { bool no_chain = false, no_chain_first = false, attn_simt = false, attn_v1 = false, attn_v2 = false, no_lnfuse = false, head_fp32 = false, no_headchain = false, no_embed_tc = false, head_prep_scalar = false, chain_dbg = false, attn_dbg = false; int ctas_per_sm = 2; bool chain_a_early = true, chain_ln_direct = true; int only = 0; } sw;      // only: energy diagnostics (results wrong on purpose): 1 = launch the attention kernels only, 2 = the layer-chain kernels only, 3 = everything but those two
+    struct Switches { bool no_chain = false, no_chain_first = false, attn_simt = false, attn_v1 = false, attn_v2 = false, no_lnfuse = false, head_fp32 = false, no_headchain = false, no_embed_tc = false, head_prep_scalar = false, head_prep_v4 = false, no_head_fused = false, chain_dbg = false, attn_dbg = false; int ctas_per_sm = 2; bool chain_a_early = true, chain_ln_direct = true; int only = 0; } sw;      // only: energy diagnostics (results wrong on purpose): 1 = launch the attention kernels only, 2 = the layer-chain kernels only, 3 = everything but those two
     // options
     int64_t pass_tokens = 0;
     int use_graph = 1;
@@ -211,7 +212,7 @@ bool split_supported(const SrhepDims& d) {
 void read_switches(SrhepHandle* h) {
     auto on = [](const char* n) { const char* v = getenv(n); return v && *v && *v != '0'; };
     h->sw.no_chain = on("SRHEP_NO_CHAIN"); h->sw.no_chain_first = on("SRHEP_NO_CHAIN_FIRST"); h->sw.attn_simt = on("SRHEP_ATTN_SIMT"); h->sw.attn_v1 = on("SRHEP_ATTN_V1"); h->sw.attn_v2 = on("SRHEP_ATTN_V2");
-    h->sw.no_lnfuse = on("SRHEP_NO_LNFUSE"); h->sw.head_fp32 = on("SRHEP_HEAD_FP32"); h->sw.no_headchain = on("SRHEP_NO_HEADCHAIN"); h->sw.no_embed_tc = on("SRHEP_NO_EMBED_TC"); h->sw.head_prep_scalar = on("SRHEP_HEAD_PREP_SCALAR");
+    h->sw.no_lnfuse = on("SRHEP_NO_LNFUSE"); h->sw.head_fp32 = on("SRHEP_HEAD_FP32"); h->sw.no_headchain = on("SRHEP_NO_HEADCHAIN"); h->sw.no_embed_tc = on("SRHEP_NO_EMBED_TC"); h->sw.head_prep_scalar = on("SRHEP_HEAD_PREP_SCALAR"); h->sw.head_prep_v4 = on("SRHEP_HEAD_PREP_V4"); h->sw.no_head_fused = on("SRHEP_NO_HEAD_FUSED");
     h->sw.chain_dbg = on("SRHEP_CHAIN_DBG"); h->sw.attn_dbg = on("SRHEP_ATTN_DBG");
     { const char* v = getenv("SRHEP_CHAIN_A_EARLY"); h->sw.chain_a_early = !(v && *v == '0'); v = getenv("SRHEP_CHAIN_LN_DIRECT"); h->sw.chain_ln_direct = !(v && *v == '0'); }
     { const char* v = getenv("SRHEP_ONLY"); h->sw.only = v ? atoi(v) : 0; }
@@ -344,6 +345,11 @@ struct Engine {
         const int grid = (q.M + 7) / 8;
         const int ph = d.h_dim / 32, pc = d.cond / 32, px = d.ctx / 32;
         if (ph == 8 && pc == 3 && px == 5 && q.x_blocked && sizeof(OutT) == 2 && q.ldt % 4 == 0 && is_lp(h) && !h->sw.head_prep_scalar) {
+            if (std::is_same<OutT, __half>::value && !hin_lo && !q.final_tap && !h->sw.head_prep_v4) {      // one reduction round per LayerNorm, two rows per round (kernels_head_fused.cuh)
+                head_prep_v5_kernel<<<(q.M + 63) / 64, 256, 0, s>>>(q, (__half*)hin, ldh);
+                check("head_prep_v5");
+                return;
+            }
             head_prep_v4_kernel<OutT><<<(q.M + 63) / 64, 256, 0, s>>>(q, hin, ldh, hin_lo);
             check("head_prep_v4");
             return;

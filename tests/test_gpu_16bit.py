@@ -135,6 +135,32 @@ def test_first_layer_chain_mode_matches_the_two_gemm_path(precision):
 
 
 @pytest.mark.parametrize("precision", ["fp16", "bf16"])
+def test_one_kernel_head_matches_the_two_launch_paths(precision):
+    """The velocity head runs as ONE kernel whose preparation warps write the operand rows straight into shared memory
+    (kernels_head_fused.cuh).  SRHEP_NO_HEAD_FUSED=1 selects the same row math as a stand-alone kernel + head_chain_kernel,
+    SRHEP_HEAD_PREP_V4=1 the round-1 preparation kernel (two-pass statistics, one row per reduction round).  Same fp16 operands,
+    fp32 sums in a different order: the velocities agree far inside the 16-bit tolerance (ragged row count, events across
+    tile edges, events shorter than the 8-row stride of a preparation warp)."""
+    m, sd, dims = make_model("single_e", 17, precision)
+    counts = np.array([124, 132, 4, 256, 804, 1, 60, 388, 7, 129])
+    batch = synthetic_events("single_e", len(counts), seed=31, counts=counts)
+    x = synthetic_noise(batch, seed=32)
+    t = torch.full((len(counts),), 0.6)
+    mask = batch["q_mask"]
+    v_one = m(to_dev(batch), x.cuda(), t.cuda()).cpu()[mask]
+    assert torch.isfinite(v_one).all()
+    for switch in ("SRHEP_NO_HEAD_FUSED", "SRHEP_HEAD_PREP_V4"):
+        os.environ[switch] = "1"
+        try:
+            v_two = m(to_dev(batch), x.cuda(), t.cuda()).cpu()[mask]
+        finally:
+            del os.environ[switch]
+        scale = float(v_two.abs().max())
+        print(f"[{precision}] one-kernel head vs {switch}: max|diff| {float((v_one - v_two).abs().max()):.3e} of {scale:.3f}")
+        torch.testing.assert_close(v_one, v_two, rtol=2e-3, atol=2e-3 * scale)
+
+
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
 def test_sharding_and_passes_are_bit_exact(precision):
     m, sd, dims = make_model("single_e", 29, precision)
     batch = synthetic_events("single_e", 96, seed=1234)
