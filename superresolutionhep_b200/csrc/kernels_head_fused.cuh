@@ -330,9 +330,9 @@ __global__ void __launch_bounds__(kHFThreads, 1) head_fused_kernel(const __grid_
                 const float* xt = q.x + (size_t)t * 128 * 256;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(xt + i * 8192), "r"(32768u) : "memory");
-                const uint32_t rows = (uint32_t)min(128, q.M - t * 128), bytes = rows * (uint32_t)q.ldt * 4u;      // ldt % 4 == 0: a multiple of 16 bytes
-                const float* ft = q.tok_feat + (size_t)t * 128 * q.ldt;
-                for (uint32_t o = 0; o < bytes; o += 32768u) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"((const uint8_t*)ft + o), "r"(min(32768u, bytes - o)) : "memory");
+                const int rows = min(128, q.M - t * 128);
+                const float* ft = q.tok_feat + (size_t)t * 128 * q.ldt;                                          // row by row: only the cond_feat columns (384 of a row's 640 bytes) are read
+                for (int r = 0; r < rows; ++r) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ft + (size_t)r * q.ldt), "r"(384u) : "memory");
             };
             if ((int)blockIdx.x < m_tiles) prefetch_tile(blockIdx.x);
             uint32_t it = 0;
