@@ -347,16 +347,14 @@ void launch_chain(Engine& E, int M, int l, const int* rev) {
     q.w[0] = bw.img + bw.out[l]; q.w[1] = bw.img + bw.mlp1[l]; q.w[2] = bw.img + bw.mlp2[l];
     const float* blh = bw.bias_h + l * bw.bias_layer_stride;
     memcpy(q.cst[0], blh, 3 * H * sizeof(float));                      // out.b | mlp1.b | mlp2.b
-    memcpy(q.cst[6], blh + 5 * H, 2 * H * sizeof(float));              // norm2 w | b
-    q.gate_msa = ml + 2 * H; q.shift_mlp = ml + 3 * H; q.scale_mlp = ml + 4 * H; q.gate_mlp = ml + 5 * H;
-    q.ld_mod = h->mod_width;
+    const float* pq = h->modpq + (size_t)l * 4 * H;                    // [P_msa | Q_msa | P_mlp | Q_mlp] of layer l (modpq_kernel)
+    q.gate_msa = ml + 2 * H; q.p_mlp = pq + 2 * H; q.q_mlp = pq + 3 * H; q.gate_mlp = ml + 5 * H;
+    q.ld_mod = h->mod_width; q.ld_pq = d.layers * 4 * H;
     if (!last) {
-        const float* mn = h->mod + (size_t)(l + 1) * 6 * H;
         for (int j = 0; j < 3; ++j) q.w[3 + j] = bw.img + bw.qkv[l + 1] + (size_t)j * H * H * 2;
         q.qkv_lo = h->qkv_lo;
         memcpy(q.cst[3], bw.bqkv_h + (size_t)(l + 1) * 3 * H, 3 * H * sizeof(float));
-        memcpy(q.cst[8], bw.bias_h + (l + 1) * bw.bias_layer_stride + 3 * H, 2 * H * sizeof(float));     // next norm1 w | b
-        q.shift_nxt = mn; q.scale_nxt = mn + H;
+        q.p_nxt = pq + 4 * H; q.q_nxt = pq + 5 * H;                        // layer l + 1: norm1 x (scale_msa, shift_msa)
         q.qkv = h->qkv_lp;
     }
     const int m_tiles = (M + 127) / 128;
@@ -401,11 +399,10 @@ void launch_chain_first(Engine& E, int M, const int* rev) {
     for (int j = 0; j < 3; ++j) q.w[1 + j] = bw.img + bw.qkv[0] + (size_t)j * H * H * 2;
     // cst[2] (bias of the residual-producing stage) stays zero: feat_0's bias is inside the per-event rows
     memcpy(q.cst[3], bw.bqkv_h, 3 * H * sizeof(float));
-    memcpy(q.cst[8], bw.bias_h + 3 * H, 2 * H * sizeof(float));        // layer 0 norm1 w | b
     q.row_bias = h->f0bias; q.ld_row_bias = H;
-    q.shift_nxt = h->mod; q.scale_nxt = h->mod + H;                    // layer 0 shift_msa | scale_msa
-    q.gate_msa = q.shift_mlp = q.scale_mlp = q.gate_mlp = h->mod;      // unused in this mode
-    q.ld_mod = h->mod_width;
+    q.p_nxt = h->modpq; q.q_nxt = h->modpq + H;                        // layer 0: norm1 x (scale_msa, shift_msa)
+    q.gate_msa = q.gate_mlp = h->mod; q.p_mlp = q.q_mlp = h->modpq;    // unused in this mode
+    q.ld_mod = h->mod_width; q.ld_pq = d.layers * 4 * H;
     q.qkv = h->qkv_lp; q.qkv_lo = h->qkv_lo;
     const int m_tiles = (M + 127) / 128;
     const int grid = std::max(1, std::min(m_tiles, (h->split ? 1 : h->sw.ctas_per_sm) * 148));

@@ -45,11 +45,14 @@ struct ChainParams {
     const uint8_t* w[6];         // pre-swizzled weight images [4 k-blocks][256 rows x 128 B]
     const uint8_t* w_lo[6];      // split mode: the low planes of the same weights
     float wscale[6];             // split mode: the images hold W * 2^s (s per matrix, so that the low plane stays out of the fp16 subnormals); this is 2^-s, applied to the accumulator
-    float cst[10][256];          // per-column constants BY VALUE (constant bank, no LSU traffic): biases of stages 0-5, norm2 w/b, next norm1 w/b
+    float cst[6][256];           // per-column constants BY VALUE (constant bank, no LSU traffic): biases of stages 0-5
     const float* gate_msa;       // per-event rows (stride ld_mod floats)
-    const float* shift_mlp; const float* scale_mlp; const float* gate_mlp;
-    const float* shift_nxt; const float* scale_nxt;       // next layer's shift_msa / scale_msa
-    int ld_mod;
+    const float* gate_mlp;
+    // LayerNorm affine and adaLN modulation combined per event by modpq_kernel:  (LN(x) w + b)(1 + scale) + shift = LN(x) P + Q  with
+    // P = w (1 + scale), Q = b (1 + scale) + shift  (stride ld_pq floats): the LayerNorm-modulate passes run on packed f32x2 instructions only
+    const float* p_mlp; const float* q_mlp;               // norm2 / (scale_mlp, shift_mlp) of this layer
+    const float* p_nxt; const float* q_nxt;               // norm1 / (scale_msa, shift_msa) of the next layer
+    int ld_mod, ld_pq;
     const float* row_bias; int ld_row_bias;   // first-layer mode only: per-event bias rows of feat_0 (its context part)
     void* qkv;                   // [M, 768] 16-bit q|k|v of the next layer
     void* qkv_lo;                // split mode: its low plane
@@ -114,21 +117,19 @@ __device__ __forceinline__ void chain_first_chunk(uint32_t (&r)[32], const float
     }
 }
 
-// r[] (bits of the residual row chunk) -> (LN(r) * w + b) * (1 + scale) + shift in place; accumulates sum / sum of squares of the
-// result as PAIRS of partial sums.  rs2 = (rstd, rstd), nm2 = (-mean rstd, -mean rstd).
-__device__ __forceinline__ void chain_ln_mod_chunk(uint32_t (&r)[32], uint64_t rs2, uint64_t nm2, const float* lw, const float* lb /*constant bank*/,
-                                                   bool staged, uint32_t sc_sm, uint32_t sh_sm, const float* __restrict__ sc, const float* __restrict__ sh,
-                                                   uint64_t& t1, uint64_t& t2) {
-    const uint64_t one2 = pack_f32x2(1.f, 1.f);
+// r[] (bits of the residual row chunk) -> LN(r) P + Q in place  (= (LN(r) w + b)(1 + scale) + shift, see ChainParams); accumulates sum /
+// sum of squares of the result as PAIRS of partial sums.  rs2 = (rstd, rstd), nm2 = (-mean rstd, -mean rstd).  Everything is packed
+// f32x2: 2.5 instructions per column (it was 5.5 with the LayerNorm weights as scalar constant-bank operands).
+__device__ __forceinline__ void chain_ln_mod_chunk(uint32_t (&r)[32], uint64_t rs2, uint64_t nm2, bool staged, uint32_t p_sm, uint32_t q_sm,
+                                                   const float* __restrict__ pg, const float* __restrict__ qg, uint64_t& t1, uint64_t& t2) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
-        const float4 s4 = par_f4(staged, sc_sm + j * 4, sc + j), h4 = par_f4(staged, sh_sm + j * 4, sh + j);
-        const uint64_t ss[2] = {fadd2(pack_f32x2(s4.x, s4.y), one2), fadd2(pack_f32x2(s4.z, s4.w), one2)}, hs[2] = {pack_f32x2(h4.x, h4.y), pack_f32x2(h4.z, h4.w)};
+        const float4 p4 = par_f4(staged, p_sm + j * 4, pg + j), q4 = par_f4(staged, q_sm + j * 4, qg + j);
+        const uint64_t pp[2] = {pack_f32x2(p4.x, p4.y), pack_f32x2(p4.z, p4.w)}, qq[2] = {pack_f32x2(q4.x, q4.y), pack_f32x2(q4.z, q4.w)};
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const uint64_t xh = ffma2(pack_f32x2(__uint_as_float(r[j + 2 * u]), __uint_as_float(r[j + 2 * u + 1])), rs2, nm2);
-            const float y0 = fmaf(f32x2_lo(xh), lw[j + 2 * u], lb[j + 2 * u]), y1 = fmaf(f32x2_hi(xh), lw[j + 2 * u + 1], lb[j + 2 * u + 1]);
-            const uint64_t y = ffma2(pack_f32x2(y0, y1), ss[u], hs[u]);
+            const uint64_t y = ffma2(xh, pp[u], qq[u]);
             t1 = fadd2(t1, y); t2 = ffma2(y, y, t2);
             r[j + 2 * u] = (uint32_t)y; r[j + 2 * u + 1] = (uint32_t)(y >> 32);
         }
@@ -194,6 +195,24 @@ __device__ __forceinline__ void transpose_line_pieces(uint32_t (&a)[32], int lan
             a[h + r] = b0 ? recv : a[h + r];
             a[h + 8 + r] = b0 ? a[h + 8 + r] : recv;
         }
+    }
+}
+
+// P = w (1 + scale), Q = b (1 + scale) + shift for LayerNorm 1 and 2 of every layer, per event: one block per event.  pq row of an
+// event: [layer][P_msa | Q_msa | P_mlp | Q_mlp][256]; mod row: [layer][shift_msa | scale_msa | gate_msa | shift_mlp | scale_mlp | gate_mlp][256];
+// nrm: per layer (stride nrm_stride) norm1.w | norm1.b | norm2.w | norm2.b (models/diffusion_transformer.py:8-9,38-52).
+struct ModPqParams { const float* mod; int ld_mod; const float* nrm; int nrm_stride; float* pq; int ld_pq; int layers; int e0; };
+__global__ void __launch_bounds__(256) modpq_kernel(ModPqParams p) {
+    const int ev = p.e0 + blockIdx.x;
+    const float* m = p.mod + (size_t)ev * p.ld_mod;
+    float* o = p.pq + (size_t)ev * p.ld_pq;
+    for (int i = threadIdx.x; i < p.layers * 2 * kChainH; i += blockDim.x) {
+        const int l = i / (2 * kChainH), w = (i / kChainH) & 1, c = i % kChainH;          // w: 0 = msa (norm1), 1 = mlp (norm2)
+        const float* ml = m + (size_t)l * 6 * kChainH + w * 3 * kChainH;
+        const float* nl = p.nrm + (size_t)l * p.nrm_stride + w * 2 * kChainH;
+        const float s1 = 1.f + ml[kChainH + c];
+        o[(size_t)l * 4 * kChainH + w * 2 * kChainH + c] = nl[c] * s1;
+        o[(size_t)l * 4 * kChainH + w * 2 * kChainH + kChainH + c] = fmaf(nl[kChainH + c], s1, ml[c]);
     }
 }
 
@@ -357,6 +376,7 @@ __global__ void __launch_bounds__(kChainThreads, kSplit ? 1 : 2) layer_chain_ker
 #define xrow (p.x + xoff)                                         /* + 1024 floats per 8-column group (32 B pieces of this row) */
             SRHEP_CHECK(!valid || (size_t)xoff + 15 * 1024 + 8 <= (size_t)((p.ext.rows_cap + 127) & ~127) * kChainH);      // last 32-byte piece of this thread's half row
             const uint32_t eo = (uint32_t)evt * (uint32_t)p.ld_mod + hh * 128;
+            const uint32_t eq = (uint32_t)evt * (uint32_t)p.ld_pq + hh * 128;
             const uint32_t psm = par_sh + (uint32_t)(evt - ev0) * 3072 + hh * 512;       // this row's event, this thread's column half, array 0
             constexpr float inv_n = 1.0f / (float)kChainH;
             // One thread copies the tile's per-event rows of three adaLN arrays into the A buffer once every MMA of the stage has
@@ -368,7 +388,7 @@ __global__ void __launch_bounds__(kChainThreads, kSplit ? 1 : 2) layer_chain_ker
                     const int na = 1 + (a1 != nullptr) + (a2 != nullptr);
                     mbar_expect_tx(par_full, (uint32_t)(ne * na) * 1024u);
                     for (int e = 0; e < ne; ++e) {
-                        const size_t go = (size_t)(ev0 + e) * p.ld_mod;
+                        const size_t go = (size_t)(ev0 + e) * p.ld_pq;
                         uint8_t* dst = s_a + 4096 + e * 3072;
                         bulk_load(dst, a0 + (size_t)(ev0 + e) * ld0, 1024, par_full);
                         if (a1) bulk_load(dst + 1024, a1 + go, 1024, par_full);
@@ -392,7 +412,7 @@ __global__ void __launch_bounds__(kChainThreads, kSplit ? 1 : 2) layer_chain_ker
                 mbar_wait(&acc_full[hh ^ 1], stage_it & 1);               // every MMA of the stage retired: the A buffer is free for the scratch and the staged rows
                 if (warp == 2 && lane == 0) CHAIN_STAMP(tile_i, 10);
                 tc_fence_after();
-                stage_rows(p.gate_msa, p.scale_mlp, p.shift_mlp, p.ld_mod);
+                stage_rows(p.gate_msa, p.p_mlp, p.q_mlp, p.ld_mod);
                 uint64_t s1p = 0ull, s2p = 0ull;
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
@@ -432,8 +452,7 @@ __global__ void __launch_bounds__(kChainThreads, kSplit ? 1 : 2) layer_chain_ker
 #pragma unroll
                         for (int j = 0; j < 32; j += 8) stg256_stream(xrow + (c * 4 + (j >> 3)) * 1024, &r[j]);      // x1
                     }
-                    chain_ln_mod_chunk(r, rs2, nm2, &p.cst[6][hh * 128 + c * 32], &p.cst[7][hh * 128 + c * 32], staged, psm + 1024 + c * 128, psm + 2048 + c * 128,
-                                       p.scale_mlp + eo + c * 32, p.shift_mlp + eo + c * 32, t1p, t2p);
+                    chain_ln_mod_chunk(r, rs2, nm2, staged, psm + 1024 + c * 128, psm + 2048 + c * 128, p.p_mlp + eq + c * 32, p.q_mlp + eq + c * 32, t1p, t2p);
                     tmem_st32(t_col + c * 32, r);
                 }
                 if (warp == 2 && lane == 0) CHAIN_STAMP(tile_i, 24);
@@ -497,7 +516,7 @@ __global__ void __launch_bounds__(kChainThreads, kSplit ? 1 : 2) layer_chain_ker
                 tc_fence_after();
                 // last layer: the A buffer is handed back to the producer (a_free) as soon as this stage's MMAs retire, so nothing may be staged in it
                 const bool st2 = staged && next;
-                if (st2) stage_rows(kFirst ? p.row_bias : p.gate_mlp, p.scale_nxt, p.shift_nxt, kFirst ? p.ld_row_bias : p.ld_mod);
+                if (st2) stage_rows(kFirst ? p.row_bias : p.gate_mlp, p.p_nxt, p.q_nxt, kFirst ? p.ld_row_bias : p.ld_mod);
                 uint64_t s1p = 0ull, s2p = 0ull;
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
@@ -544,8 +563,7 @@ __global__ void __launch_bounds__(kChainThreads, kSplit ? 1 : 2) layer_chain_ker
 #pragma unroll
                                 for (int j = 0; j < 32; j += 8) stg256_stream(xrow + (c * 4 + (j >> 3)) * 1024, &r[j]);      // x2
                             }
-                            chain_ln_mod_chunk(r, rs2, nm2, &p.cst[8][hh * 128 + c * 32], &p.cst[9][hh * 128 + c * 32], staged, psm + 1024 + c * 128, psm + 2048 + c * 128,
-                                               p.scale_nxt + eo + c * 32, p.shift_nxt + eo + c * 32, t1p, t2p);
+                            chain_ln_mod_chunk(r, rs2, nm2, staged, psm + 1024 + c * 128, psm + 2048 + c * 128, p.p_nxt + eq + c * 32, p.q_nxt + eq + c * 32, t1p, t2p);
                             uint32_t pk[16];
 #pragma unroll
                             for (int j = 0; j < 32; j += 2) pk[j >> 1] = pack16(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), fp16);
@@ -561,8 +579,7 @@ __global__ void __launch_bounds__(kChainThreads, kSplit ? 1 : 2) layer_chain_ker
 #pragma unroll
                                 for (int j = 0; j < 32; j += 8) stg256_stream(xrow + (c * 4 + (j >> 3)) * 1024, &r[j]);      // x2
                             }
-                            chain_ln_mod_chunk(r, rs2, nm2, &p.cst[8][hh * 128 + c * 32], &p.cst[9][hh * 128 + c * 32], staged, psm + 1024 + c * 128, psm + 2048 + c * 128,
-                                               p.scale_nxt + eo + c * 32, p.shift_nxt + eo + c * 32, t1p, t2p);
+                            chain_ln_mod_chunk(r, rs2, nm2, staged, psm + 1024 + c * 128, psm + 2048 + c * 128, p.p_nxt + eq + c * 32, p.q_nxt + eq + c * 32, t1p, t2p);
 #pragma unroll
                             for (int j = 0; j < 32; j += 2) held[c * 16 + (j >> 1)] = pack16(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), fp16);
                             if (hh != 0) chain_store_a_packed(a_sh, rt, hh * 128 + c * 32, &held[c * 16]);
@@ -579,8 +596,7 @@ __global__ void __launch_bounds__(kChainThreads, kSplit ? 1 : 2) layer_chain_ker
 #pragma unroll
                             for (int j = 0; j < 32; j += 8) stg256_stream(xrow + (c * 4 + (j >> 3)) * 1024, &r[j]);      // x2
                         }
-                        chain_ln_mod_chunk(r, rs2, nm2, &p.cst[8][hh * 128 + c * 32], &p.cst[9][hh * 128 + c * 32], staged, psm + 1024 + c * 128, psm + 2048 + c * 128,
-                                           p.scale_nxt + eo + c * 32, p.shift_nxt + eo + c * 32, t1p, t2p);
+                        chain_ln_mod_chunk(r, rs2, nm2, staged, psm + 1024 + c * 128, psm + 2048 + c * 128, p.p_nxt + eq + c * 32, p.q_nxt + eq + c * 32, t1p, t2p);
                         tmem_st32(t_col + c * 32, r);
                     }
                     tmem_st_wait();

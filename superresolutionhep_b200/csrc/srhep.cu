@@ -139,6 +139,7 @@ struct SrhepHandle {
     // per-event buffers [B, .]
     float *temb = nullptr, *ev_a = nullptr, *ev_stats = nullptr, *layer_out = nullptr, *ctx = nullptr, *silu_ctx = nullptr;
     float *mod = nullptr, *f0bias = nullptr, *partial = nullptr, *t_fill = nullptr;
+    float* modpq = nullptr;             // [B, layers * 4 * h_dim]   P | Q vectors of every LayerNorm-modulate of the layer chain (kernels_chain.cuh: modpq_kernel)
     // per-pass workspace [max_pass_rows, .]
     float *tok_feat = nullptr, *xres = nullptr, *qkv = nullptr, *h1buf = nullptr;
     void *act_a = nullptr, *act_b = nullptr;      // GEMM A operands (fp32 or bf16): ln_out / attn_out / mlp hidden / head in
@@ -450,6 +451,12 @@ struct Engine {
                 GemmEpilogue ep; ep.bias = h->bmod;
                 gemm_f32<float>(sc, d.ctx, h->wmod, d.ctx, mo, h->mod_width, nE, h->mod_width, d.ctx, ep);
             }
+            if (h->modpq && h->bw.bias && !rc) {      // LayerNorm affine x adaLN modulation of every layer as one multiply-add per column for the layer chain
+                ModPqParams q;
+                q.mod = h->mod; q.ld_mod = h->mod_width; q.nrm = h->bw.bias + 3 * (size_t)d.h_dim; q.nrm_stride = (int)h->bw.bias_layer_stride;
+                q.pq = h->modpq; q.ld_pq = d.layers * 4 * kChainH; q.layers = d.layers; q.e0 = p.e0;
+                modpq_kernel<<<nE, 256, 0, s>>>(q); check("modpq");
+            }
             GemmEpilogue e2; e2.bias = W(L.feat0.b);
             gemm_f32<float>(h->ctx + (size_t)p.e0 * d.ctx, d.ctx, W(L.feat0.w) + ncol, L.feat0.in, h->f0bias + (size_t)p.e0 * d.h_dim, d.h_dim,
                             nE, d.h_dim, d.ctx, e2);
@@ -573,6 +580,7 @@ int alloc_for_binding(SrhepHandle* h) {
     if ((rc = dev_alloc(h, h->ctx, B * d.ctx))) return rc;
     if ((rc = dev_alloc(h, h->silu_ctx, B * d.ctx))) return rc;
     if ((rc = dev_alloc(h, h->mod, B * h->mod_width))) return rc;
+    if (h->bw.bias && h->d.h_dim == kChainH && (rc = dev_alloc(h, h->modpq, B * (size_t)h->d.layers * 4 * kChainH))) return rc;
     if ((rc = dev_alloc(h, h->f0bias, B * d.h_dim))) return rc;
     if ((rc = dev_alloc(h, h->t_fill, B))) return rc;
     if ((rc = dev_alloc(h, h->ev_chunk_start, B + 1))) return rc;
@@ -816,7 +824,7 @@ int srhep_destroy(SrhepHandle* h) {
     cudaDeviceSynchronize();
     drop_graphs(h);
     void* ptrs[] = {h->w, h->wqkv, h->bqkv, h->wmod, h->bmod, h->mod_tbias, h->r1, h->cu_dev, h->row_event, h->chunk_event, h->chunk_row, h->chunk_len,
-                    h->ev_chunk_start, h->attn_work, h->temb, h->ev_a, h->ev_stats, h->layer_out, h->ctx, h->silu_ctx, h->mod, h->f0bias,
+                    h->ev_chunk_start, h->attn_work, h->temb, h->ev_a, h->ev_stats, h->layer_out, h->ctx, h->silu_ctx, h->mod, h->modpq, h->f0bias,
                     h->partial, h->t_fill, h->tok_feat, h->xres, h->qkv, h->h1buf, h->act_a, h->act_b, h->qkv_lp, h->qkv_lo, h->act_b_lo, h->y_a, h->y_b, h->y_tmp,
                     h->ybuf2, h->red_dev, h->sp_dev, h->stage_idx_dev, h->tap_layers, h->tap_feat0, h->tap_final};
     for (void* p : ptrs) if (p) cudaFree(p);

@@ -114,8 +114,11 @@ def test_tensor_core_attention_matches_simt_attention():
 @pytest.mark.parametrize("precision", ["fp16", "bf16"])
 def test_first_layer_chain_mode_matches_the_two_gemm_path(precision):
     """feat_0 -> LN1.modulate -> layer-0 q|k|v runs as ONE launch of the chain kernel (first-layer mode); SRHEP_NO_CHAIN_FIRST=1
-    selects the two tcgen05 GEMM launches it replaced.  Same operands and the same fp32 epilogue math in a different
-    reduction order: the velocities must agree far inside the 16-bit tolerance (ragged row count, events across tile edges)."""
+    selects the two tcgen05 GEMM launches it replaced.  Same operands; the fp32 epilogue math differs in reduction order and, since the
+    chain kernel applies the LayerNorm affine and the adaLN modulation as ONE multiply-add per column (P = w (1 + scale),
+    Q = b (1 + scale) + shift, modpq_kernel), by an ulp per element: the velocities must agree far inside the 16-bit tolerance
+    (ragged row count, events across tile edges).  An fp32 ulp can flip the 16-bit rounding of a LayerNorm output: with bf16 operands
+    (2^-8) a single flipped element moves a velocity by up to 6e-3 of max|v|, so bf16 is held to half its single-evaluation bound."""
     m, sd, dims = make_model("single_e", 13, precision)
     counts = np.array([124, 132, 4, 256, 804, 60, 388])
     batch = synthetic_events("single_e", len(counts), seed=21, counts=counts)
@@ -131,7 +134,8 @@ def test_first_layer_chain_mode_matches_the_two_gemm_path(precision):
     scale = float(v_two.abs().max())
     print(f"[{precision}] first-layer chain vs two GEMMs: max|diff| {float((v_fused - v_two).abs().max()):.3e} of {scale:.3f}")
     assert torch.isfinite(v_fused).all()
-    torch.testing.assert_close(v_fused, v_two, rtol=5e-3, atol=5e-3 * scale)
+    tol = 5e-3 if precision == "fp16" else 1.5e-2
+    torch.testing.assert_close(v_fused, v_two, rtol=tol, atol=tol * scale)
 
 
 @pytest.mark.parametrize("precision", ["fp16", "bf16"])
