@@ -173,7 +173,14 @@ int bf16_pack_weights(SrhepHandle* h, const float* wh) {
     std::vector<float> b(bw.bias_fn + 2 * (size_t)H + 2 * (size_t)d.v_in);
     for (int l = 0; l < d.layers; ++l) {
         const Layout::Layer& y = L.layers[l];
-        memcpy(&b[l * bw.bias_layer_stride], wh + y.o.b, H * sizeof(float));
+        // out-projection bias + W_o b_v: the tcgen05 paths project V WITHOUT its bias (every attention row's weights sum to 1, so the value
+        // bias reaches the out-projection unchanged) and K without its bias (a key bias adds the same q . b_k to every score of a row: the
+        // softmax cancels it).  Exact in real arithmetic; models/attention.py:112-123, 238-265.
+        for (int i = 0; i < H; ++i) {
+            double acc = wh[y.o.b + i];
+            for (int j = 0; j < H; ++j) acc += (double)wh[y.o.w + (size_t)i * H + j] * (double)wh[y.v.b + j];
+            b[l * bw.bias_layer_stride + i] = (float)acc;
+        }
         memcpy(&b[l * bw.bias_layer_stride + H], wh + y.m1.b, H * sizeof(float));
         memcpy(&b[l * bw.bias_layer_stride + 2 * H], wh + y.m2.b, H * sizeof(float));
         memcpy(&b[l * bw.bias_layer_stride + 3 * H], wh + y.n1w, H * sizeof(float));
@@ -192,8 +199,13 @@ int bf16_pack_weights(SrhepHandle* h, const float* wh) {
     memcpy(bw.bias_h, b.data(), b.size() * sizeof(float));
     for (int l = 0; l < d.layers; ++l) {
         const Lin* qkv[3] = {&L.layers[l].q, &L.layers[l].k, &L.layers[l].v};
-        for (int j = 0; j < 3; ++j) memcpy(bw.bqkv_h + ((size_t)l * 3 + j) * H, wh + qkv[j]->b, H * sizeof(float));
+        for (int j = 0; j < 3; ++j) {
+            if (j == 0) memcpy(bw.bqkv_h + ((size_t)l * 3 + j) * H, wh + qkv[j]->b, H * sizeof(float));
+            else memset(bw.bqkv_h + ((size_t)l * 3 + j) * H, 0, H * sizeof(float));          // K, V: see the out-projection bias above
+        }
     }
+    CK(h, cudaMalloc(&bw.bqkv_dev, (size_t)d.layers * 3 * H * sizeof(float)));
+    CK(h, cudaMemcpy(bw.bqkv_dev, bw.bqkv_h, (size_t)d.layers * 3 * H * sizeof(float), cudaMemcpyHostToDevice));
     CK(h, cudaFuncSetAttribute(gemm_bf16_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_bf16_smem_bytes<256>(4)));
     CK(h, cudaFuncSetAttribute(gemm_bf16_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_bf16_smem_bytes<256>(4)));
     CK(h, cudaFuncSetAttribute(attn_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmemBytes));
@@ -230,6 +242,7 @@ void bf16_free_weights(SrhepHandle* h) {
     if (h->bw.img_lo) cudaFree(h->bw.img_lo);
     if (h->bw.tok_lp_lo) cudaFree(h->bw.tok_lp_lo);
     if (h->bw.bias) cudaFree(h->bw.bias);
+    if (h->bw.bqkv_dev) cudaFree(h->bw.bqkv_dev);
     if (h->bw.tok_lp) cudaFree(h->bw.tok_lp);
     free(h->bw.bias_h); free(h->bw.bqkv_h);
     delete static_cast<EmbedTcParams*>(h->bw.embed_tpl);
@@ -448,7 +461,7 @@ void bf16_forward(Engine& E, const Pass& p, const int* rev, const StageRef& st) 
         // layer 0's q|k|v come from the feat_0 GEMM's fused LN1; every later projection rides in the previous layer's chain kernel
         E.cat = SRHEP_CAT_QKV;
         if (!first_fused)
-        { GemmEpilogue ep; ep.bias = h->bqkv;
+        { GemmEpilogue ep; ep.bias = bw.bqkv_dev;
           launch_gemm_bf16<256>(E, bw.tm_ln, M, H, 3 * H, bw.img + bw.qkv[0], qkv, 3 * H, 1, ep); }
         for (int l = 0; l < d.layers; ++l) {
             E.cat = SRHEP_CAT_ATTN;
@@ -463,7 +476,7 @@ void bf16_forward(Engine& E, const Pass& p, const int* rev, const StageRef& st) 
         const float* ml = mod + (size_t)l * 6 * H;
         const float* bl = bw.bias + l * bw.bias_layer_stride;
         E.cat = SRHEP_CAT_QKV;
-        { GemmEpilogue ep; ep.bias = h->bqkv + (size_t)l * 3 * H;
+        { GemmEpilogue ep; ep.bias = bw.bqkv_dev + (size_t)l * 3 * H;
           launch_gemm_bf16<256>(E, bw.tm_ln, M, H, 3 * H, bw.img + bw.qkv[l], qkv, 3 * H, 1, ep); }
         E.cat = SRHEP_CAT_ATTN;
         if (!fp16 && h->sw.attn_simt) E.attention_simt<__nv_bfloat16>(p, qkv, b);

@@ -947,7 +947,8 @@ struct Bf16Weights {
     size_t qkv[64] = {0}, out[64] = {0}, mlp1[64] = {0}, mlp2[64] = {0};
     float* bias = nullptr;           // 16-byte aligned copies: per layer [out | mlp1 | mlp2], then head1
     float* bias_h = nullptr;         // host mirror of `bias` (per-column constants travel by value into the chain kernel)
-    float* bqkv_h = nullptr;         // host mirror of the stacked q|k|v biases
+    float* bqkv_h = nullptr;         // host mirror of the stacked q|k|v biases as the tcgen05 paths use them: q's kept, k's and v's zero (folded away, bf16_forward.inl)
+    float* bqkv_dev = nullptr;       // the same on the device (epilogues of the unfused q|k|v GEMMs)
     size_t bias_layer_stride = 0, bias_head1 = 0, bias_fn = 0;     // bias_fn: final_norm w | b | norm_v_t w | b (16-byte aligned copies)
     __nv_bfloat16* tok_lp = nullptr; // [rows, feat0 K padded] bf16 copy of tok_feat (feat_0 GEMM A operand)
     int feat0_kpad = 0;

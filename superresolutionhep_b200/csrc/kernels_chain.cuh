@@ -100,12 +100,12 @@ __device__ __forceinline__ void chain_resid_chunk(uint32_t (&r)[32], const float
 
 // first-layer mode: leaky(acc + bias + per-event bias) IS the residual row (feat_0, models/flow_model.py:224-228)
 template <bool kScaled = false>
-__device__ __forceinline__ void chain_first_chunk(uint32_t (&r)[32], const float* bias /*constant bank*/, bool staged, uint32_t rb_sm, const float* __restrict__ rb,
+__device__ __forceinline__ void chain_first_chunk(uint32_t (&r)[32], const float* /*bias: zero in this mode*/, bool staged, uint32_t rb_sm, const float* __restrict__ rb,
                                                   uint64_t& s1, uint64_t& s2, float ws = 1.f) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
         const float4 b4 = par_f4(staged, rb_sm + j * 4, rb + j);
-        const float bb[4] = {bias[j] + b4.x, bias[j + 1] + b4.y, bias[j + 2] + b4.z, bias[j + 3] + b4.w};
+        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};            // feat_0's own bias is inside the per-event rows (gemm of the context part): no per-column constant to add
 #pragma unroll
         for (int u = 0; u < 4; u += 2) {
             const float w0 = leaky_relu(kScaled ? fmaf(__uint_as_float(r[j + u]), ws, bb[u]) : __uint_as_float(r[j + u]) + bb[u]);
@@ -206,13 +206,16 @@ __global__ void __launch_bounds__(256) modpq_kernel(ModPqParams p) {
     const int ev = p.e0 + blockIdx.x;
     const float* m = p.mod + (size_t)ev * p.ld_mod;
     float* o = p.pq + (size_t)ev * p.ld_pq;
-    for (int i = threadIdx.x; i < p.layers * 2 * kChainH; i += blockDim.x) {
-        const int l = i / (2 * kChainH), w = (i / kChainH) & 1, c = i % kChainH;          // w: 0 = msa (norm1), 1 = mlp (norm2)
+    for (int i = threadIdx.x; i < p.layers * 2 * (kChainH / 4); i += blockDim.x) {       // four columns per thread and step (all rows are 16-byte aligned)
+        const int l = i / (2 * (kChainH / 4)), w = (i / (kChainH / 4)) & 1, c = (i % (kChainH / 4)) * 4;      // w: 0 = msa (norm1), 1 = mlp (norm2)
         const float* ml = m + (size_t)l * 6 * kChainH + w * 3 * kChainH;
         const float* nl = p.nrm + (size_t)l * p.nrm_stride + w * 2 * kChainH;
-        const float s1 = 1.f + ml[kChainH + c];
-        o[(size_t)l * 4 * kChainH + w * 2 * kChainH + c] = nl[c] * s1;
-        o[(size_t)l * 4 * kChainH + w * 2 * kChainH + kChainH + c] = fmaf(nl[kChainH + c], s1, ml[c]);
+        const float4 sh = *reinterpret_cast<const float4*>(ml + c), sc = *reinterpret_cast<const float4*>(ml + kChainH + c);
+        const float4 nw = *reinterpret_cast<const float4*>(nl + c), nb = *reinterpret_cast<const float4*>(nl + kChainH + c);
+        const float4 s1 = make_float4(1.f + sc.x, 1.f + sc.y, 1.f + sc.z, 1.f + sc.w);
+        float* ol = o + (size_t)l * 4 * kChainH + w * 2 * kChainH + c;
+        *reinterpret_cast<float4*>(ol) = make_float4(nw.x * s1.x, nw.y * s1.y, nw.z * s1.z, nw.w * s1.w);
+        *reinterpret_cast<float4*>(ol + kChainH) = make_float4(fmaf(nb.x, s1.x, sh.x), fmaf(nb.y, s1.y, sh.y), fmaf(nb.z, s1.z, sh.z), fmaf(nb.w, s1.w, sh.w));
     }
 }
 
@@ -494,8 +497,14 @@ __global__ void __launch_bounds__(kChainThreads, kSplit ? 1 : 2) layer_chain_ker
                     tmem_ld_wait();
                     const float* b = &p.cst[1][hh * 128 + c * 32];
                     float v[32];
+                    const uint64_t slope2 = pack_f32x2(kLeaky, kLeaky);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = leaky_relu(kSplit ? fmaf(__uint_as_float(r[j]), p.wscale[1], b[j]) : __uint_as_float(r[j]) + b[j]);
+                    for (int j = 0; j < 32; j += 2) {                       // LeakyReLU = max(x, 0.01 x), the product on a packed instruction
+                        const float w0 = kSplit ? fmaf(__uint_as_float(r[j]), p.wscale[1], b[j]) : __uint_as_float(r[j]) + b[j];
+                        const float w1 = kSplit ? fmaf(__uint_as_float(r[j + 1]), p.wscale[1], b[j + 1]) : __uint_as_float(r[j + 1]) + b[j + 1];
+                        const uint64_t lk = fmul2(pack_f32x2(w0, w1), slope2);
+                        v[j] = fmaxf(w0, f32x2_lo(lk)); v[j + 1] = fmaxf(w1, f32x2_hi(lk));
+                    }
                     if (kSplit) chain_store_a_split(a_sh, rt, hh * 128 + c * 32, v); else chain_store_a(a_sh, rt, hh * 128 + c * 32, v, fp16);
                 }
                 stage_done(true);
@@ -637,16 +646,35 @@ __global__ void __launch_bounds__(kChainThreads, kSplit ? 1 : 2) layer_chain_ker
                             tmem_ld_wait();
                             const float* b = &p.cst[3 + g][hh * 128 + c * 32];
                             const float ws = p.wscale[kFirst ? 1 + g : 3 + g];
+                            if (g == 0) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 2) {
                                 if (kSplit) split16(fmaf(__uint_as_float(r[j]), ws, b[j]), fmaf(__uint_as_float(r[j + 1]), ws, b[j + 1]), a[half * 16 + (j >> 1)], al[kSplit ? half * 16 + (j >> 1) : 0]);
                                 else a[half * 16 + (j >> 1)] = pack16(__uint_as_float(r[j]) + b[j], __uint_as_float(r[j + 1]) + b[j + 1], fp16);
                             }
+                            } else {
+                            // K and V carry no bias here: a key bias shifts every score of a query row by the same q . b_k, which the softmax cancels, and
+                            // the value bias passes through the attention unchanged (the weights of a row sum to 1), so it sits in the out-projection's bias
+                            // (b_o + W_o b_v, folded when the weights are packed: bf16_forward.inl).  One add and one constant load per element less.
+#pragma unroll
+                            for (int j = 0; j < 32; j += 2) {
+                                if (kSplit) split16(__uint_as_float(r[j]) * ws, __uint_as_float(r[j + 1]) * ws, a[half * 16 + (j >> 1)], al[kSplit ? half * 16 + (j >> 1) : 0]);
+                                else a[half * 16 + (j >> 1)] = pack16(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), fp16);
+                            }
+                            }
                         }
+#ifdef SRHEP_QKV_ROW_STORES       // A/B: every lane stores the 128-byte line of ITS row as four 32-byte pieces (no transposes, four times the LSU wavefronts)
+                        if (valid) {
+                            uint16_t* drow = reinterpret_cast<uint16_t*>(p.qkv) + (size_t)row * (3 * kChainH) + g * kChainH + hh * 128 + blk * 64;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) stg256(drow + i * 16, &a[8 * i]);
+                        }
+#else
                         transpose_line_pieces(a, lane);
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
                             if (row4 + i < p.M) { SRHEP_CHECK(row4 + i < p.ext.rows_cap); stg256(dst + (size_t)i * (3 * kChainH) + blk * 64, &a[8 * i]); }
+#endif
                         if constexpr (kSplit) {
                             transpose_line_pieces(al, lane);
                             uint16_t* dlo = reinterpret_cast<uint16_t*>(p.qkv_lo) + doff;
