@@ -15,7 +15,7 @@ launches)  CMD="python bench.py --steps 1 --warmup 3 --no-extra --no-cpu-baselin
            $CMD > $O/${TAG}_short.json 2>> $O/${TAG}_bench.err && timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches.csv $CMD > $O/${TAG}_ncu_launches.log 2>&1 ;;
 full)      CMD="python bench.py --steps 1 --warmup 3 --no-extra --no-cpu-baseline"
            # one evaluation's worth of the hot kernels: skip the launches of the first evaluations (graph capture / warm-up), then 20 launches
-           $CMD > /dev/null 2>> $O/${TAG}_bench.err && timeout 1200 ncu --set full --clock-control none -k regex:'embed_tc|context_rows|gemm_f32_big|layer_chain|attn3|head_' -s 120 -c 18 -f -o $O/${TAG}_full $CMD > $O/${TAG}_ncu_full.log 2>&1
+           $CMD > /dev/null 2>> $O/${TAG}_bench.err && timeout 1200 ncu --set full --clock-control none -k regex:'embed_tc|context_rows|gemm_f32_big|modpq|layer_chain|attn3|head_' -s 126 -c 19 -f -o $O/${TAG}_full $CMD > $O/${TAG}_ncu_full.log 2>&1
            # the report itself (source view of 18 launches) is larger than what gpurun copies back: keep the per-launch counter summary
            python tools/ncu_summary.py $O/${TAG}_full.ncu-rep > $O/${TAG}_ncu_kernels.csv 2>> $O/${TAG}_bench.err; rm -f $O/${TAG}_full.ncu-rep
            tail -2 $O/${TAG}_ncu_full.log; wc -l $O/${TAG}_ncu_kernels.csv ;;

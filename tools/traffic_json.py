@@ -16,7 +16,7 @@ scale = {"[Gbyte]": 1e9, "[Mbyte]": 1e6, "[Kbyte]": 1e3, "[byte]": 1.0}
 sr = [v for k, v in scale.items() if k in h[rd]][0]
 sw = [v for k, v in scale.items() if k in h[wr]][0]
 # kernel -> (category, launches per evaluation); the capture window may hold a kernel of the neighbouring evaluation too: averages per kernel, then the counts
-kern = {"embed_tc": ("embed", 1), "context_rows": ("embed", 1), "gemm_f32_big": ("adaln", 1), "attn3": ("attn", None), "head_fused": ("head", 1),
+kern = {"embed_tc": ("embed", 1), "context_rows": ("embed", 1), "gemm_f32_big": ("adaln", 1), "modpq": ("adaln", 1), "attn3": ("attn", None), "head_fused": ("head", 1),
         "head_prep": ("head", 1), "head_chain": ("head", 1), "layer_chain_kernel<1, 1": ("feat0", 1), "layer_chain_kernel<0, 1": ("feat0", 1), "layer_chain_kernel": ("chain", None)}
 seen = {}
 for r in rows[1:]:
