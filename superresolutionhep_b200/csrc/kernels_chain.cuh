@@ -490,11 +490,7 @@ __global__ void __launch_bounds__(kChainThreads, kSplit ? 1 : 2) layer_chain_ker
                 mbar_wait(&acc_full[hh ^ 1], stage_it & 1);               // A is rewritten in place: every MMA of the stage must have retired
                 if (warp == 2 && lane == 0) CHAIN_STAMP(tile_i, 12);
                 tc_fence_after();
-#pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t r[32];
-                    tmem_ld32(t_col + c * 32, r);
-                    tmem_ld_wait();
+                auto hidden_chunk = [&](const uint32_t (&r)[32], int c) {
                     const float* b = &p.cst[1][hh * 128 + c * 32];
                     float v[32];
                     const uint64_t slope2 = pack_f32x2(kLeaky, kLeaky);
@@ -506,6 +502,28 @@ __global__ void __launch_bounds__(kChainThreads, kSplit ? 1 : 2) layer_chain_ker
                         v[j] = fmaxf(w0, f32x2_lo(lk)); v[j + 1] = fmaxf(w1, f32x2_hi(lk));
                     }
                     if (kSplit) chain_store_a_split(a_sh, rt, hh * 128 + c * 32, v); else chain_store_a(a_sh, rt, hh * 128 + c * 32, v, fp16);
+                };
+#ifdef SRHEP_CHAIN_TMEM_PIPE      // A/B: the tensor-memory read of chunk c + 1 in flight under the arithmetic of chunk c (two register buffers)
+                if constexpr (!kSplit) {
+                    uint32_t ra[32], rb[32];
+                    tmem_ld32(t_col, ra);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        if (c < 3) { if (c & 1) tmem_ld32(t_col + (c + 1) * 32, ra); else tmem_ld32(t_col + (c + 1) * 32, rb); }
+                        if (c & 1) hidden_chunk(rb, c); else hidden_chunk(ra, c);
+                        if (c < 3) tmem_ld_wait();
+                    }
+                } else
+#endif
+                {
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t r[32];
+                    tmem_ld32(t_col + c * 32, r);
+                    tmem_ld_wait();
+                    hidden_chunk(r, c);
+                }
                 }
                 stage_done(true);
             }
@@ -638,12 +656,18 @@ __global__ void __launch_bounds__(kChainThreads, kSplit ? 1 : 2) layer_chain_ker
 #pragma unroll 1
                     for (int blk = 0; blk < 2; ++blk) {
                         uint32_t a[32], al[kSplit ? 32 : 1];
+                        uint32_t rr[2][32];
+#ifdef SRHEP_CHAIN_TMEM_PIPE      // A/B: both halves of the 64-column block requested at once (one wait instead of two dependent read / wait pairs)
+                        constexpr bool kBoth = !kSplit;
+                        if (kBoth) { tmem_ld32(t_col + blk * 64, rr[0]); tmem_ld32(t_col + blk * 64 + 32, rr[1]); tmem_ld_wait(); }
+#else
+                        constexpr bool kBoth = false;
+#endif
 #pragma unroll
                         for (int half = 0; half < 2; ++half) {
                             const int c = blk * 2 + half;
-                            uint32_t r[32];
-                            tmem_ld32(t_col + c * 32, r);
-                            tmem_ld_wait();
+                            uint32_t (&r)[32] = rr[half];
+                            if (!kBoth) { tmem_ld32(t_col + c * 32, r); tmem_ld_wait(); }
                             const float* b = &p.cst[3 + g][hh * 128 + c * 32];
                             const float ws = p.wscale[kFirst ? 1 + g : 3 + g];
                             if (g == 0) {
