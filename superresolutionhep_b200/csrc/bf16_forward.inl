@@ -353,6 +353,7 @@ void launch_chain(Engine& E, int M, int l, const int* rev) {
     ChainParams q{};
     q.M = M; q.n_stages = last ? 3 : 6; q.fp16 = h->precision == SRHEP_PREC_FP16; q.a_early = h->sw.chain_a_early; q.ln_direct = h->sw.chain_ln_direct;
     q.ext.rows_cap = (int)h->cap_ws_rows; q.ext.n_events = h->B;
+    q.a_pf = h->sw.chain_a_pf;                                       // SRHEP_CHAIN_A_PF: measured at slots 8 / 24 / 32 / 40, never a gain: off by default
 #ifdef SRHEP_BOUNDS
     if (getenv("SRHEP_BOUNDS_SELFTEST")) q.ext.rows_cap = 1;      // tests/test_gpu_bounds.py: proves that a violated extent is caught (the kernel traps)
 #endif
@@ -408,6 +409,7 @@ void launch_chain_first(Engine& E, int M, const int* rev) {
     q.M = M; q.n_stages = 4; q.fp16 = h->precision == SRHEP_PREC_FP16; q.a_early = h->sw.chain_a_early; q.ln_direct = h->sw.chain_ln_direct;
     q.ext.rows_cap = (int)h->cap_ws_rows; q.ext.n_events = h->B;
     q.row_event = rev; q.x = h->xres;
+    q.a_pf = h->sw.chain_a_pf;
     q.w[0] = bw.img + bw.feat0;
     for (int j = 0; j < 3; ++j) q.w[1 + j] = bw.img + bw.qkv[0] + (size_t)j * H * H * 2;
     // cst[2] (bias of the residual-producing stage) stays zero: feat_0's bias is inside the per-event rows

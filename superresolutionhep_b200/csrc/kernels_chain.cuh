@@ -60,6 +60,8 @@ struct ChainParams {
     Extents ext;                 // checked in the -DSRHEP_BOUNDS build only
     int a_early;                 // release the A buffer k-block by k-block (1 in production; 0 = after the tile's last MMA, for A/B runs)
     int ln_direct;               // stage 2: LayerNorm output straight to A (1 in production; 0 = parked in TMEM and copied in a third pass, for A/B runs)
+    int a_pf;                    // weight-slot index of a tile at which the producer pulls the NEXT tile's A operand into L2 (-1 = never).  The L2 turns
+                                 // over every ~70 k cycles under this kernel's traffic: a whole tile period ahead is too early, the last stages are not
 };
 
 __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
@@ -297,6 +299,11 @@ __global__ void __launch_bounds__(kChainThreads, kSplit ? 1 : 2) layer_chain_ker
                         for (int i = 0; i < 4; ++i)
                             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(xt + i * 8192), "r"(32768u) : "memory");
                         }
+                    }
+                    if (j == p.a_pf && t + (int)gridDim.x < m_tiles) {        // the next tile's A operand (attention output, 64 KB): towards L2 now, into shared memory when this tile's last MMAs retire
+#pragma unroll
+                        for (int kb2 = 0; kb2 < kKb0; ++kb2)
+                            asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(&tmap_a), "r"(kb2 * 64), "r"((t + (int)gridDim.x) * 128) : "memory");
                     }
                     int g, nh, kb;                                            // column half outer: the two halves of the accumulator are a double buffer
                     if (kFirst && j < 6) { g = 0; nh = j / 3; kb = j % 3; }

@@ -118,7 +118,7 @@ struct SrhepHandle {
     int mod_width = 0;
 
     // diagnostic switches (environment, read once per API call: A/B comparisons in the tests and tools)
-    struct Switches { bool no_chain = false, no_chain_first = false, attn_simt = false, attn_v1 = false, attn_v2 = false, no_lnfuse = false, head_fp32 = false, no_headchain = false, no_embed_tc = false, head_prep_scalar = false, head_prep_v4 = false, no_head_fused = false, chain_dbg = false, attn_dbg = false; int ctas_per_sm = 2; bool chain_a_early = true, chain_ln_direct = true; int only = 0; } sw;      // only: energy diagnostics (results wrong on purpose): 1 = launch the attention kernels only, 2 = the layer-chain kernels only, 3 = everything but those two
+    struct Switches { bool no_chain = false, no_chain_first = false, attn_simt = false, attn_v1 = false, attn_v2 = false, no_lnfuse = false, head_fp32 = false, no_headchain = false, no_embed_tc = false, head_prep_scalar = false, head_prep_v4 = false, no_head_fused = false, chain_dbg = false, attn_dbg = false; int ctas_per_sm = 2; bool chain_a_early = true, chain_ln_direct = true; int chain_a_pf = -1; int only = 0; } sw;      // only: energy diagnostics (results wrong on purpose): 1 = launch the attention kernels only, 2 = the layer-chain kernels only, 3 = everything but those two
     // options
     int64_t pass_tokens = 0;
     int use_graph = 1;
@@ -216,6 +216,7 @@ void read_switches(SrhepHandle* h) {
     h->sw.no_lnfuse = on("SRHEP_NO_LNFUSE"); h->sw.head_fp32 = on("SRHEP_HEAD_FP32"); h->sw.no_headchain = on("SRHEP_NO_HEADCHAIN"); h->sw.no_embed_tc = on("SRHEP_NO_EMBED_TC"); h->sw.head_prep_scalar = on("SRHEP_HEAD_PREP_SCALAR"); h->sw.head_prep_v4 = on("SRHEP_HEAD_PREP_V4"); h->sw.no_head_fused = on("SRHEP_NO_HEAD_FUSED");
     h->sw.chain_dbg = on("SRHEP_CHAIN_DBG"); h->sw.attn_dbg = on("SRHEP_ATTN_DBG");
     { const char* v = getenv("SRHEP_CHAIN_A_EARLY"); h->sw.chain_a_early = !(v && *v == '0'); v = getenv("SRHEP_CHAIN_LN_DIRECT"); h->sw.chain_ln_direct = !(v && *v == '0'); }
+    { const char* v = getenv("SRHEP_CHAIN_A_PF"); h->sw.chain_a_pf = v ? atoi(v) : -1; }      // -1 (default): no L2 prefetch of the next A tile; else the weight-slot index of a tile at which it is issued
     { const char* v = getenv("SRHEP_ONLY"); h->sw.only = v ? atoi(v) : 0; }
     { const char* v = getenv("SRHEP_CTAS_PER_SM"); h->sw.ctas_per_sm = (v && *v == '1') ? 1 : 2; }      // persistent grids of the chain / attention kernels: CTAs per SM
 }
